@@ -1,0 +1,1 @@
+"""Empty import stub, see matplotlib/__init__.py."""
