@@ -1,0 +1,121 @@
+/*
+ * pymra_b200 C ABI -- the drop-in boundary for pyMRA's MRATree hot path on B200 (sm_100a).
+ *
+ * The reference (marcinjurek/pyMRA) is pure Python and has no FFI of its own; the
+ * boundary it exposes is the class MRATree (pyMRA/MRATree.py:20-94).  The host-side
+ * mirror pymra_b200.MRATree keeps that class' signature and calls the entry points
+ * below through ctypes.  Each entry point names the reference code it replaces.
+ *
+ * Conventions: every function returns 0 on success and a negative mra_status on
+ * failure, never throws across the ABI, and leaves a message retrievable with
+ * mra_last_error().  The caller owns every buffer it passes in.  One handle per
+ * device; a handle is not thread-safe.  Host pointers unless the name says "dev".
+ * There is no CPU fallback: without a CUDA device mra_create fails.
+ */
+#ifndef PYMRA_B200_H
+#define PYMRA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mra_handle mra_handle;
+
+enum mra_status {
+  MRA_OK = 0,
+  MRA_ERR_ARG = -1,        /* bad argument / unsupported configuration */
+  MRA_ERR_CUDA = -2,       /* CUDA runtime error */
+  MRA_ERR_STATE = -3,      /* call order violated */
+  MRA_ERR_NOT_SPD = -4,    /* a Cholesky factorisation met a non-positive pivot */
+  MRA_ERR_NOMEM = -5       /* workspace too small */
+};
+
+enum mra_cov_family {      /* pyMRA/MRATools.py */
+  MRA_COV_EXP = 0,         /* ExpCovFun  :265-269   exp(-D/l)                          */
+  MRA_COV_MATERN32 = 1     /* Matern32   :289-293   sig*(1+sqrt(3)D/l)*exp(-sqrt(3)D/l) */
+};
+
+enum mra_node_kind { MRA_NODE_INTERNAL = 0, MRA_NODE_LEAF = 1, MRA_NODE_ORPHAN = 2 };
+
+/* Flat tree description in "tree order" (pymra_b200/structure.py).  It carries exactly the
+ * information the reference keeps in Node.inds / Node.kInds / Node.children
+ * (pyMRA/MRANode.py:32, 38-45, 69, 98). Nodes are numbered level by level, children of a node
+ * are consecutive, every node owns rows [row_start, row_start+row_count). */
+typedef struct mra_structure {
+  int64_t n_locs;                 /* N                                             */
+  int32_t dim;                    /* 1 or 2                                        */
+  int32_t r;                      /* knots per internal node (MRATree r)           */
+  int32_t depth;                  /* deepest level present (root = 0)              */
+  int32_t n_nodes;
+  const int32_t *node_level;      /* [n_nodes]                                     */
+  const int32_t *node_parent;     /* [n_nodes] -1 for the root                     */
+  const int32_t *node_kind;       /* [n_nodes] mra_node_kind                       */
+  const int64_t *node_row_start;  /* [n_nodes]                                     */
+  const int64_t *node_row_count;  /* [n_nodes]                                     */
+  const int32_t *node_child_start;/* [n_nodes] -1 if none                          */
+  const int32_t *node_child_count;/* [n_nodes]                                     */
+  const int64_t *node_knot_off;   /* [n_nodes] offset into knot_rows, -1 for leaves */
+  const int64_t *knot_rows;       /* [n_knot_rows] tree-order row ids, r per internal node */
+  int64_t n_knot_rows;
+  const int32_t *level_off;       /* [depth+2] node id ranges per level            */
+  const int64_t *perm;            /* [N] tree position -> caller's row index       */
+} mra_structure;
+
+/* Lifetime.  Replaces: construction/destruction of the Python MRATree object. */
+int mra_create(mra_handle **out, int device);
+int mra_destroy(mra_handle *h);
+const char *mra_last_error(const mra_handle *h);
+const char *mra_version(void);
+
+/* Tree/knot/partition indexing computed on the host (bit-exact to MRANode.py:23-98,
+ * 179-242, 289-340); copied into the handle. */
+int mra_set_structure(mra_handle *h, const mra_structure *s);
+
+/* Scans the NaN pattern of obs (MRANode.py:415, np.isfinite) and sizes the device workspace.
+ * obs: [N] in the caller's order.  want_predict != 0 reserves the buffers predict() needs. */
+int mra_plan(mra_handle *h, const double *obs, int want_predict, size_t *workspace_bytes);
+
+/* Device arena of at least workspace_bytes (256-byte aligned), owned by the caller
+ * (a torch uint8 tensor in the Python host). */
+int mra_bind_workspace(mra_handle *h, void *dev_workspace, size_t bytes);
+
+/* locs: [N*dim] row-major (MRATree locs), obs: [N] with NaN = missing (MRATree obs).
+ * Host buffers; copied H2D on `stream` and permuted to tree order on the device. */
+int mra_upload_data(mra_handle *h, const double *locs, const double *obs, void *stream);
+
+/* Covariance descriptor introspected from the mt.ExpCovFun / mt.Matern32 closure, and the
+ * nugget R (MRATree R / me_scale; must be a scalar, MRANode.py:85-88). */
+int mra_set_cov(mra_handle *h, int family, double length_scale, double sig);
+int mra_set_nugget(mra_handle *h, double R);
+
+/* Prior pass + leaf terms + upward pass (MRANode.py:378-395, 403-480).
+ * out[0] = root.d, out[1] = root.u; getLikelihood() = out[0] + out[1] (MRATree.py:82-84). */
+int mra_run_likelihood(mra_handle *h, void *stream, double out[2]);
+
+/* Downward pass (MRANode.py:486-520).  mean, sd: [N] host buffers in the caller's order
+ * (MRATree.py:90-94: root.mean, sqrt(root.var)).  Requires mra_run_likelihood first. */
+int mra_run_predict(mra_handle *h, void *stream, double *mean, double *sd);
+
+/* Same as the two calls above but without the final device->host copies / with results left
+ * on the device (used by bench.py's device-resident timing).  dev_mean/dev_sd may be NULL. */
+int mra_run_likelihood_async(mra_handle *h, void *stream);
+int mra_run_predict_dev(mra_handle *h, void *stream, double *dev_mean, double *dev_sd);
+int mra_fetch_likelihood(mra_handle *h, void *stream, double out[2]);
+
+/* Counters for bench.py: kernels launched by the last run_* call, and algorithmic FP64
+ * flop of the last likelihood / predict pass as executed. */
+int mra_last_launches(const mra_handle *h, int64_t *n);
+int mra_last_flops(const mra_handle *h, double *likelihood_flops, double *predict_flops);
+
+/* Test hook: copies an internal device buffer to the host.
+ * what: "V" (N x ldv, node ignored), "A", "GT", "LPINV", "LINV", "VK" (per node), "dnode" (all nodes).
+ * Returns the number of doubles written (<= max_doubles) or a negative status. */
+int64_t mra_debug_fetch(mra_handle *h, const char *what, int node, double *out, int64_t max_doubles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYMRA_B200_H */

@@ -1,0 +1,105 @@
+"""Covariance closure -> device covariance descriptor.
+
+The reference takes `cov` as an arbitrary Python callable `(locs1, locs2) -> np.matrix`
+(pyMRA/MRANode.py:77-80, 384).  The device evaluates two families, mt.ExpCovFun and mt.Matern32
+(pyMRA/MRATools.py:265-269, 289-293), possibly scaled by a constant.  The closure is probed
+numerically, its family and parameters are recovered in closed form, and the result is verified
+on random location pairs; anything that does not verify raises (there is no CPU fallback).
+"""
+import math
+
+import numpy as np
+
+from ._ffi import COV_EXP, COV_MATERN32
+
+_S3 = math.sqrt(3.0)
+
+
+class CovDescriptor(object):
+    __slots__ = ("family", "l", "sig")
+
+    def __init__(self, family, l, sig=1.0):
+        self.family, self.l, self.sig = int(family), float(l), float(sig)
+
+    @property
+    def name(self):
+        return "exp" if self.family == COV_EXP else "matern32"
+
+    def __call__(self, D):
+        D = np.asarray(D, dtype=np.float64)
+        if self.family == COV_EXP:
+            return self.sig * np.exp(-D / self.l)
+        t = _S3 * D / self.l
+        return self.sig * ((1 + t) * np.exp(-t))
+
+    def __repr__(self):
+        return "CovDescriptor(%s, l=%r, sig=%r)" % (self.name, self.l, self.sig)
+
+
+def _eval(cov, a, b):
+    out = np.asarray(cov(a, b), dtype=np.float64)
+    if out.shape != (len(a), len(b)):
+        raise ValueError("cov(locs1, locs2) returned shape %s, expected %s" % (out.shape, (len(a), len(b))))
+    return out
+
+
+def _solve_matern_t(g):
+    """t > 0 with (1+t)exp(-t) = g, 0 < g < 1."""
+    lo, hi = 0.0, 1.0
+    while (1 + hi) * math.exp(-hi) > g:
+        hi *= 2.0
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if (1 + mid) * math.exp(-mid) > g:
+            lo = mid
+        else:
+            hi = mid
+    t = 0.5 * (lo + hi)
+    for _ in range(4):       # Newton polish
+        f = (1 + t) * math.exp(-t) - g
+        t -= f / (-t * math.exp(-t))
+    return t
+
+
+def introspect(cov, d, rtol=1e-12, n_check=512, seed=12345):
+    """Return the CovDescriptor of `cov`, or raise ValueError / NotImplementedError."""
+    if isinstance(cov, CovDescriptor):
+        return cov
+    if isinstance(cov, np.ndarray):      # np.matrix included (MRANode.py:73-75, 381-382)
+        raise NotImplementedError("a dense covariance matrix as `cov` is outside the accelerated path; "
+                                  "pass an mt.ExpCovFun / mt.Matern32 closure")
+    if not callable(cov):
+        raise TypeError("cov must be a callable (locs1, locs2) -> matrix")
+    dists = np.array([0.0] + [10.0 ** e for e in np.arange(-4.0, 2.01, 0.25)])
+    pts = np.zeros((len(dists), d))
+    pts[:, 0] = dists
+    row = _eval(cov, pts[:1], pts)[0]
+    c0 = row[0]
+    if not (np.isfinite(c0) and c0 > 0):
+        raise ValueError("cov(x, x) must be positive and finite")
+    g = row / c0
+    ok = np.flatnonzero((g > 0.2) & (g < 0.8))
+    if not len(ok):
+        ok = np.flatnonzero((g > 1e-3) & (g < 1 - 1e-6))
+    if not len(ok):
+        raise ValueError("could not probe the covariance closure (no distance with 0 < c(d)/c(0) < 1)")
+    k = ok[len(ok) // 2]
+    cands = [CovDescriptor(COV_EXP, -dists[k] / math.log(g[k]), c0),
+             CovDescriptor(COV_MATERN32, _S3 * dists[k] / _solve_matern_t(g[k]), c0)]
+    rng = np.random.RandomState(seed)
+    a = rng.uniform(0, 1, size=(n_check, d))
+    b = rng.uniform(0, 1, size=(n_check, d)) * rng.choice([1e-3, 1e-1, 1.0, 5.0], size=(n_check, 1))
+    want = np.concatenate((row, np.diag(_eval(cov, a, a + b)),
+                           _eval(cov, a[:8], a[:8]).ravel()))
+    Dcheck = np.concatenate((dists, np.sqrt((b * b).sum(axis=1)),
+                             np.sqrt(((a[:8, None, :] - a[None, :8, :]) ** 2).sum(axis=2)).ravel()))
+    errs = []
+    for cand in cands:
+        got = cand(Dcheck)
+        err = np.max(np.abs(got - want) / c0)
+        errs.append(err)
+        if err <= rtol:
+            return cand
+    raise ValueError("cov is not an ExpCovFun/Matern32 closure (mismatch exp %.2e, matern32 %.2e relative); "
+                     "other covariance functions are outside the accelerated path and there is no CPU fallback"
+                     % (errs[0], errs[1]))

@@ -1,0 +1,633 @@
+// Host runtime and C ABI of pymra_b200 (see include/pymra_b200.h).
+//
+// The handle owns no device memory of its own: every device buffer is carved out of the arena
+// the caller binds with mra_bind_workspace (a torch tensor in the Python host).
+#include "../../include/pymra_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mra_kernels.cuh"
+
+using namespace mra;
+
+namespace {
+
+struct Arena {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~size_t(255);
+    return o;
+  }
+};
+
+struct Layout {
+  size_t nodes, knot_rows, obs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
+      mean, var, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles;
+  size_t total;
+};
+
+}  // namespace
+
+struct mra_handle {
+  int device = 0;
+  std::string err;
+  bool has_structure = false, planned = false, bound = false, uploaded = false, lik_done = false,
+       pred_done = false, want_predict = false;
+  // structure
+  int64_t N = 0;
+  int dim = 0, r = 0, depth = 0, n_nodes = 0;
+  std::vector<int> level, parent, kind, child_start, child_count, level_off;
+  std::vector<int64_t> row_start, row_count, knot_off;
+  std::vector<int> knot_rows, perm;
+  // derived lists
+  std::vector<std::vector<int>> internal_at;   // node ids per level
+  std::vector<int> leaves;                     // node ids of leaves + orphans
+  std::vector<std::vector<int4>> tiles_at;     // 64-row tiles of internal nodes per level
+  std::vector<NodeDev> nodes;
+  std::vector<int> obs_rows;
+  int max_leaf_obs = 0, max_leaf_rows = 0, max_leaf_W = 1;
+  int64_t n_obs_total = 0;
+  long long ldv = 0;
+  // device
+  Layout lay{};
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  std::vector<size_t> list_off, tiles_off;   // per level offsets (bytes) inside lay.lists / lay.tiles
+  size_t leaves_off = 0;
+  CovParams cov{0, 1.0, 1.0, 1.0};
+  double R = 1.0;
+  bool cov_set = false, R_set = false;
+  int64_t launches = 0;
+  double flops_lik = 0, flops_pred = 0;
+};
+
+namespace {
+
+int fail(mra_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(h, MRA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+template <class T>
+T* at(mra_handle* h, size_t off) {
+  return reinterpret_cast<T*>(h->ws + off);
+}
+
+DevCtx make_ctx(mra_handle* h) {
+  DevCtx c{};
+  const Layout& L = h->lay;
+  c.nodes = at<NodeDev>(h, L.nodes);
+  c.knot_rows = at<int>(h, L.knot_rows);
+  c.obs_rows = at<int>(h, L.obs_rows);
+  c.xs = at<double>(h, L.xs);
+  c.ys = at<double>(h, L.ys);
+  c.yobs = at<double>(h, L.yobs);
+  c.V = at<double>(h, L.V);
+  c.ldv = h->ldv;
+  c.r = h->r;
+  c.N = (int)h->N;
+  c.S = at<double>(h, L.S);
+  c.DI = at<double>(h, L.DI);
+  c.UT = at<double>(h, L.UT);
+  c.QT = at<double>(h, L.QT);
+  c.A = at<double>(h, L.A);
+  c.GT = at<double>(h, L.GT);
+  c.LPINV = at<double>(h, L.LPINV);
+  c.VK = at<double>(h, L.VK);
+  c.LINV = at<double>(h, L.LINV);
+  c.dnode = at<double>(h, L.dnode);
+  c.mean = at<double>(h, L.mean);
+  c.var = at<double>(h, L.var);
+  c.status = at<int>(h, L.status);
+  c.cov = h->cov;
+  c.R = h->R;
+  return c;
+}
+
+size_t smem_knot(int r) { return sizeof(double) * ((size_t)r * (r + 1) + 3 * r + 2 * TB * LDT) + sizeof(int) * r + 16; }
+size_t smem_prior(int r) {
+  int ldT = ((r + 15) / 16) * 16 + 4;
+  return sizeof(double) * ((size_t)TB * ldT + 2 * TB * LDT + 2 * r + 2 * TB);
+}
+size_t smem_chol() { return sizeof(double) * ((size_t)2 * TB * LDB + TB + 2 * TB * LDT); }
+size_t smem_solve() { return sizeof(double) * ((size_t)TB * LDB + 2 * TB * LDT); }
+size_t smem_factor(int r) { return sizeof(double) * ((size_t)r * (r + 1) + r + 2 * TB * LDT); }
+size_t smem_predict(int r) {
+  int ldT = ((r + 15) / 16) * 16 + 4;
+  return sizeof(double) * ((size_t)TB * ldT + 2 * TB * LDT);
+}
+
+int configure_kernels(mra_handle* h) {
+  const int r = h->r;
+  CU(cudaFuncSetAttribute(k_knot_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_knot(r)));
+  CU(cudaFuncSetAttribute(k_prior_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prior(r)));
+  CU(cudaFuncSetAttribute(k_leaf_chol_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol()));
+  CU(cudaFuncSetAttribute(k_leaf_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve()));
+  CU(cudaFuncSetAttribute(k_node_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_factor(r)));
+  CU(cudaFuncSetAttribute(k_predict_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_predict(r)));
+  return MRA_OK;
+}
+
+int check_status(mra_handle* h, cudaStream_t st) {
+  int flag = 0;
+  CU(cudaMemcpyAsync(&flag, at<int>(h, h->lay.status), sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (flag != 0)
+    return fail(h, MRA_ERR_NOT_SPD, "a Cholesky factorisation met a non-positive pivot (covariance not positive definite)");
+  return MRA_OK;
+}
+
+int launch_likelihood(mra_handle* h, cudaStream_t st) {
+  const Layout& L = h->lay;
+  DevCtx c = make_ctx(h);
+  const int r = h->r;
+  h->launches = 0;
+  CU(cudaMemsetAsync(at<double>(h, L.dnode), 0, sizeof(double) * h->n_nodes, st));
+  CU(cudaMemsetAsync(at<int>(h, L.status), 0, sizeof(int), st));
+  // ---- prior, top-down
+  for (int m = 0; m < (int)h->internal_at.size(); ++m) {
+    const int nn = (int)h->internal_at[m].size();
+    if (!nn) continue;
+    const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
+    k_knot_factor<<<nn, NT, smem_knot(r), st>>>(c, list);
+    ++h->launches;
+    const int ntile = (int)h->tiles_at[m].size();
+    const int4* tiles = reinterpret_cast<const int4*>(h->ws + L.tiles + h->tiles_off[m]);
+    k_prior_tiles<<<ntile, NT, smem_prior(r), st>>>(c, tiles, m);
+    ++h->launches;
+  }
+  // ---- leaves
+  const int nleaf = (int)h->leaves.size();
+  const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off);
+  if (nleaf && h->max_leaf_obs > 0) {
+    const int nbo = (h->max_leaf_obs + TB - 1) / TB;
+    dim3 g1(nleaf, nbo * (nbo + 1) / 2);
+    k_leaf_gram<<<g1, NT, 0, st>>>(c, leaf_list, 0);
+    ++h->launches;
+    for (int p = 0; p < nbo; ++p) {
+      dim3 g2(nleaf, nbo - p);
+      k_leaf_chol_step<<<g2, NT, smem_chol(), st>>>(c, leaf_list, p);
+      ++h->launches;
+    }
+    dim3 g3(nleaf, (h->max_leaf_W + TB - 1) / TB);
+    k_leaf_solve<<<g3, NT, smem_solve(), st>>>(c, leaf_list, 0);
+    ++h->launches;
+  }
+  // ---- upward
+  for (int m = (int)h->internal_at.size() - 1; m >= 0; --m) {
+    const int nn = (int)h->internal_at[m].size();
+    if (!nn) continue;
+    const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
+    const int W = (m + 1) * r + 1, nb = (W + TB - 1) / TB;
+    dim3 ga(nn, nb * (nb + 1) / 2);
+    k_assemble_A<<<ga, NT, 0, st>>>(c, list);
+    ++h->launches;
+    dim3 gf(nn, (m * r + 1 + TB - 1) / TB);
+    k_node_factor<<<gf, NT, smem_factor(r), st>>>(c, list);
+    ++h->launches;
+  }
+  k_finalize<<<1, NT, 0, st>>>(c, at<double>(h, L.out));
+  ++h->launches;
+  CU(cudaGetLastError());
+  h->lik_done = true;
+  h->pred_done = false;
+  return MRA_OK;
+}
+
+int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev_sd) {
+  const Layout& L = h->lay;
+  DevCtx c = make_ctx(h);
+  const int r = h->r;
+  if (!h->pred_done) {
+    const int nleaf = (int)h->leaves.size();
+    const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off);
+    k_resid_var<<<nleaf, 256, 0, st>>>(c, leaf_list);
+    ++h->launches;
+    if (h->max_leaf_obs > 0) {
+      const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
+      dim3 g1(nleaf, nbr * nbo);
+      k_leaf_gram<<<g1, NT, 0, st>>>(c, leaf_list, 1);
+      ++h->launches;
+      dim3 g2(nleaf, nbr);
+      k_leaf_solve<<<g2, NT, smem_solve(), st>>>(c, leaf_list, 1);
+      ++h->launches;
+      dim3 g3(nleaf, nbr * ((h->max_leaf_W + TB - 1) / TB));
+      k_leaf_apply<<<g3, NT, 0, st>>>(c, leaf_list);
+      ++h->launches;
+    }
+    for (int m = (int)h->internal_at.size() - 1; m >= 0; --m) {
+      const int ntile = (int)h->tiles_at[m].size();
+      if (!ntile) continue;
+      const int4* tiles = reinterpret_cast<const int4*>(h->ws + L.tiles + h->tiles_off[m]);
+      k_predict_level<<<ntile, NT, smem_predict(r), st>>>(c, tiles, m);
+      ++h->launches;
+    }
+    h->pred_done = true;   // V now holds the posterior-updated basis; results stay cached in mean/var
+  }
+  const int N = (int)h->N;
+  k_unpermute<<<(N + 255) / 256, 256, 0, st>>>(c.mean, c.var, at<int>(h, L.perm), N,
+                                               dev_mean ? dev_mean : at<double>(h, L.out_mean),
+                                               dev_sd ? dev_sd : at<double>(h, L.out_sd));
+  ++h->launches;
+  CU(cudaGetLastError());
+  return MRA_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* mra_version(void) { return "pymra_b200 0.1 (sm_100a)"; }
+
+int mra_create(mra_handle** out, int device) {
+  if (!out) return MRA_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return MRA_ERR_CUDA;
+  mra_handle* h = new (std::nothrow) mra_handle();
+  if (!h) return MRA_ERR_NOMEM;
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete h;
+    return MRA_ERR_CUDA;
+  }
+  *out = h;
+  return MRA_OK;
+}
+
+int mra_destroy(mra_handle* h) {
+  delete h;
+  return MRA_OK;
+}
+
+const char* mra_last_error(const mra_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int mra_set_structure(mra_handle* h, const mra_structure* s) {
+  if (!h || !s) return MRA_ERR_ARG;
+  if (s->n_locs <= 0 || s->n_locs >= (int64_t(1) << 31)) return fail(h, MRA_ERR_ARG, "n_locs out of range");
+  if (s->dim != 1 && s->dim != 2) return fail(h, MRA_ERR_ARG, "dim must be 1 or 2");
+  if (s->r < 1 || s->r > 128) return fail(h, MRA_ERR_ARG, "r must be in [1, 128] in this build");
+  if (s->n_nodes < 1 || s->depth < 0) return fail(h, MRA_ERR_ARG, "empty tree");
+  h->N = s->n_locs;
+  h->dim = s->dim;
+  h->r = s->r;
+  h->depth = s->depth;
+  h->n_nodes = s->n_nodes;
+  const int nn = s->n_nodes;
+  h->level.assign(s->node_level, s->node_level + nn);
+  h->parent.assign(s->node_parent, s->node_parent + nn);
+  h->kind.assign(s->node_kind, s->node_kind + nn);
+  h->row_start.assign(s->node_row_start, s->node_row_start + nn);
+  h->row_count.assign(s->node_row_count, s->node_row_count + nn);
+  h->child_start.assign(s->node_child_start, s->node_child_start + nn);
+  h->child_count.assign(s->node_child_count, s->node_child_count + nn);
+  h->knot_off.assign(s->node_knot_off, s->node_knot_off + nn);
+  h->level_off.assign(s->level_off, s->level_off + s->depth + 2);
+  h->knot_rows.resize(s->n_knot_rows);
+  for (int64_t i = 0; i < s->n_knot_rows; ++i) {
+    if (s->knot_rows[i] < 0 || s->knot_rows[i] >= h->N) return fail(h, MRA_ERR_ARG, "knot row out of range");
+    h->knot_rows[i] = (int)s->knot_rows[i];
+  }
+  h->perm.resize(h->N);
+  for (int64_t i = 0; i < h->N; ++i) {
+    if (s->perm[i] < 0 || s->perm[i] >= h->N) return fail(h, MRA_ERR_ARG, "perm entry out of range");
+    h->perm[i] = (int)s->perm[i];
+  }
+  h->internal_at.assign(s->depth + 1, {});
+  h->tiles_at.assign(s->depth + 1, {});
+  h->leaves.clear();
+  for (int n = 0; n < nn; ++n) {
+    const int lv = h->level[n];
+    if (lv < 0 || lv > s->depth) return fail(h, MRA_ERR_ARG, "node level out of range");
+    if (h->row_start[n] < 0 || h->row_start[n] + h->row_count[n] > h->N)
+      return fail(h, MRA_ERR_ARG, "node row range out of bounds");
+    if (h->kind[n] == KIND_INTERNAL) {
+      if (h->knot_off[n] < 0 || h->knot_off[n] + h->r > s->n_knot_rows)
+        return fail(h, MRA_ERR_ARG, "internal node without r knots");
+      if (h->child_count[n] <= 0) return fail(h, MRA_ERR_ARG, "internal node without children");
+      h->internal_at[lv].push_back(n);
+      for (int64_t r0 = 0; r0 < h->row_count[n]; r0 += TB)
+        h->tiles_at[lv].push_back(make_int4(n, (int)(h->row_start[n] + r0),
+                                            (int)std::min<int64_t>(TB, h->row_count[n] - r0), 0));
+    } else {
+      h->leaves.push_back(n);
+    }
+  }
+  while (!h->internal_at.empty() && h->internal_at.back().empty()) {
+    h->internal_at.pop_back();
+    h->tiles_at.pop_back();
+  }
+  h->ldv = std::max<long long>(2, ((long long)std::max(h->depth, 1) * h->r + 1) / 2 * 2);
+  h->has_structure = true;
+  h->planned = h->bound = h->uploaded = h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspace_bytes) {
+  if (!h || !obs || !workspace_bytes) return MRA_ERR_ARG;
+  if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
+  const int nn = h->n_nodes, r = h->r;
+  h->want_predict = want_predict != 0;
+  h->nodes.assign(nn, NodeDev{});
+  h->obs_rows.clear();
+  long long s_off = 0, di_off = 0, ut_off = 0, qt_off = 0, a_off = 0, gt_off = 0, lp_off = 0, vk_off = 0,
+            linv_off = 0;
+  h->max_leaf_obs = h->max_leaf_rows = 0;
+  h->max_leaf_W = 1;
+  double f_lik = 0, f_pred = 0;
+  for (int n = 0; n < nn; ++n) {
+    NodeDev& d = h->nodes[n];
+    d.level = h->level[n];
+    d.kind = h->kind[n];
+    d.parent = h->parent[n];
+    d.child_start = h->child_start[n];
+    d.child_count = h->child_count[n];
+    d.row_start = (int)h->row_start[n];
+    d.row_count = (int)h->row_count[n];
+    d.knot_off = (int)h->knot_off[n];
+    d.W = d.level * r + 1;
+    const double Kv = (double)d.level * r;
+    if (d.kind == KIND_INTERNAL) {
+      const int Wa = (d.level + 1) * r + 1;
+      d.lda = (Wa + 3) / 4 * 4;
+      d.a_off = a_off;
+      a_off += (long long)Wa * d.lda;
+      d.gt_off = gt_off;
+      gt_off += (long long)d.W * r;
+      d.lpinv_off = lp_off;
+      lp_off += (long long)r * r;
+      d.linv_off = linv_off;
+      linv_off += (long long)r * r;
+      d.vk_off = vk_off;
+      vk_off += (long long)r * d.level * r;
+      const double nr = (double)d.row_count;
+      f_lik += 2.0 * r * r * Kv + r * (double)r * r / 3.0;           // knot covariance + factor
+      f_lik += 2.0 * nr * r * Kv + nr * r * (double)r;              // prior rows + whitening
+      f_lik += (double)r * r * r / 3.0 + 2.0 * r * r * Kv / 1.0;    // node factor + G
+      f_lik += (double)(Kv + 1) * (Kv + 1) * r;                     // Schur complement (symmetric half)
+      f_pred += nr * r * (double)r + 2.0 * nr * r * Kv;             // t and basis update
+    } else {
+      d.obs_off = (int)h->obs_rows.size();
+      if (d.kind == KIND_LEAF) {
+        for (int64_t i = 0; i < h->row_count[n]; ++i) {
+          const int64_t row = h->row_start[n] + i;
+          if (std::isfinite(obs[h->perm[row]])) h->obs_rows.push_back((int)row);
+        }
+      }
+      d.n_obs = (int)h->obs_rows.size() - d.obs_off;
+      d.ldo = std::max(4, (d.n_obs + 3) / 4 * 4);
+      const int nb = (d.n_obs + TB - 1) / TB;
+      d.s_off = s_off;
+      s_off += (long long)d.n_obs * d.ldo;
+      d.di_off = di_off;
+      di_off += (long long)nb * TB * TB;
+      d.ut_off = ut_off;
+      ut_off += (long long)d.W * d.ldo;
+      d.qt_off = qt_off;
+      if (h->want_predict) qt_off += (long long)d.row_count * d.ldo;
+      h->max_leaf_obs = std::max(h->max_leaf_obs, d.n_obs);
+      h->max_leaf_rows = std::max(h->max_leaf_rows, d.row_count);
+      if (d.n_obs > 0) h->max_leaf_W = std::max(h->max_leaf_W, d.W);
+      const double no = d.n_obs, nl = d.row_count;
+      f_lik += no * no * Kv + no * no * no / 3.0 + no * no * (Kv + 1) + no * (Kv + 1) * (Kv + 1);
+      f_pred += 2.0 * no * nl * Kv + no * no * nl + 2.0 * nl * no * (Kv + 1);
+    }
+  }
+  h->n_obs_total = (int64_t)h->obs_rows.size();
+  h->flops_lik = f_lik;
+  h->flops_pred = f_pred;
+  // ---- arena layout
+  Arena ar;
+  Layout& L = h->lay;
+  const size_t N = (size_t)h->N, D = sizeof(double);
+  L.nodes = ar.take(sizeof(NodeDev) * nn);
+  L.knot_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->knot_rows.size()));
+  L.obs_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->obs_rows.size()));
+  L.perm = ar.take(sizeof(int) * N);
+  L.xs = ar.take(D * N);
+  L.ys = ar.take(D * N);
+  L.yobs = ar.take(D * N);
+  L.V = ar.take(D * N * (size_t)h->ldv);
+  L.S = ar.take(D * std::max<long long>(1, s_off));
+  L.DI = ar.take(D * std::max<long long>(1, di_off));
+  L.UT = ar.take(D * std::max<long long>(1, ut_off));
+  L.QT = ar.take(D * std::max<long long>(1, qt_off));
+  L.A = ar.take(D * std::max<long long>(1, a_off));
+  L.GT = ar.take(D * std::max<long long>(1, gt_off));
+  L.LPINV = ar.take(D * std::max<long long>(1, lp_off));
+  L.VK = ar.take(D * std::max<long long>(1, vk_off));
+  L.LINV = ar.take(D * std::max<long long>(1, linv_off));
+  L.dnode = ar.take(D * nn);
+  L.mean = ar.take(D * N);
+  L.var = ar.take(D * N);
+  L.status = ar.take(256);
+  L.out = ar.take(256);
+  L.stage_locs = ar.take(D * N * h->dim);
+  L.stage_obs = ar.take(D * N);
+  L.out_mean = ar.take(D * N);
+  L.out_sd = ar.take(D * N);
+  h->list_off.assign(h->internal_at.size(), 0);
+  h->tiles_off.assign(h->internal_at.size(), 0);
+  size_t lo = 0, to = 0;
+  for (size_t m = 0; m < h->internal_at.size(); ++m) {
+    h->list_off[m] = lo;
+    lo += (sizeof(int) * h->internal_at[m].size() + 255) & ~size_t(255);
+    h->tiles_off[m] = to;
+    to += (sizeof(int4) * h->tiles_at[m].size() + 255) & ~size_t(255);
+  }
+  h->leaves_off = lo;
+  lo += (sizeof(int) * h->leaves.size() + 255) & ~size_t(255);
+  L.lists = ar.take(std::max<size_t>(256, lo));
+  L.tiles = ar.take(std::max<size_t>(256, to));
+  L.total = ar.off;
+  *workspace_bytes = L.total;
+  h->planned = true;
+  h->bound = h->uploaded = h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+int mra_bind_workspace(mra_handle* h, void* dev_workspace, size_t bytes) {
+  if (!h || !dev_workspace) return MRA_ERR_ARG;
+  if (!h->planned) return fail(h, MRA_ERR_STATE, "mra_plan must be called first");
+  if (bytes < h->lay.total) return fail(h, MRA_ERR_NOMEM, "workspace smaller than mra_plan reported");
+  if (reinterpret_cast<uintptr_t>(dev_workspace) % 256) return fail(h, MRA_ERR_ARG, "workspace must be 256-byte aligned");
+  CU(cudaSetDevice(h->device));
+  h->ws = static_cast<char*>(dev_workspace);
+  h->ws_bytes = bytes;
+  int rc = configure_kernels(h);
+  if (rc) return rc;
+  h->bound = true;
+  h->uploaded = h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+int mra_upload_data(mra_handle* h, const double* locs, const double* obs, void* stream) {
+  if (!h || !locs || !obs) return MRA_ERR_ARG;
+  if (!h->bound) return fail(h, MRA_ERR_STATE, "mra_bind_workspace must be called first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Layout& L = h->lay;
+  const size_t N = (size_t)h->N;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->ws + L.nodes, h->nodes.data(), sizeof(NodeDev) * h->nodes.size(), cudaMemcpyHostToDevice, st));
+  if (!h->knot_rows.empty())
+    CU(cudaMemcpyAsync(h->ws + L.knot_rows, h->knot_rows.data(), sizeof(int) * h->knot_rows.size(), cudaMemcpyHostToDevice, st));
+  if (!h->obs_rows.empty())
+    CU(cudaMemcpyAsync(h->ws + L.obs_rows, h->obs_rows.data(), sizeof(int) * h->obs_rows.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->ws + L.perm, h->perm.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+  for (size_t m = 0; m < h->internal_at.size(); ++m) {
+    if (!h->internal_at[m].empty())
+      CU(cudaMemcpyAsync(h->ws + L.lists + h->list_off[m], h->internal_at[m].data(),
+                         sizeof(int) * h->internal_at[m].size(), cudaMemcpyHostToDevice, st));
+    if (!h->tiles_at[m].empty())
+      CU(cudaMemcpyAsync(h->ws + L.tiles + h->tiles_off[m], h->tiles_at[m].data(),
+                         sizeof(int4) * h->tiles_at[m].size(), cudaMemcpyHostToDevice, st));
+  }
+  if (!h->leaves.empty())
+    CU(cudaMemcpyAsync(h->ws + L.lists + h->leaves_off, h->leaves.data(), sizeof(int) * h->leaves.size(),
+                       cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->ws + L.stage_locs, locs, sizeof(double) * N * h->dim, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->ws + L.stage_obs, obs, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+  k_permute_inputs<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(
+      at<double>(h, L.stage_locs), at<double>(h, L.stage_obs), at<int>(h, L.perm), (int)N, h->dim,
+      at<double>(h, L.xs), at<double>(h, L.ys), at<double>(h, L.yobs));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));   // host vectors may change after return
+  h->uploaded = true;
+  h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+int mra_set_cov(mra_handle* h, int family, double length_scale, double sig) {
+  if (!h) return MRA_ERR_ARG;
+  if (family != MRA_COV_EXP && family != MRA_COV_MATERN32) return fail(h, MRA_ERR_ARG, "unknown covariance family");
+  if (!(length_scale > 0.0) || !(sig > 0.0)) return fail(h, MRA_ERR_ARG, "length scale and sig must be positive");
+  h->cov.family = family;
+  h->cov.l = length_scale;
+  h->cov.sig = sig;
+  h->cov.c0 = h->cov.sig;
+  h->cov_set = true;
+  h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+int mra_set_nugget(mra_handle* h, double R) {
+  if (!h) return MRA_ERR_ARG;
+  if (!(R > 0.0)) return fail(h, MRA_ERR_ARG, "R must be a positive scalar");
+  h->R = R;
+  h->R_set = true;
+  h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+int mra_run_likelihood_async(mra_handle* h, void* stream) {
+  if (!h) return MRA_ERR_ARG;
+  if (!h->uploaded) return fail(h, MRA_ERR_STATE, "mra_upload_data must be called first");
+  if (!h->cov_set || !h->R_set) return fail(h, MRA_ERR_STATE, "mra_set_cov and mra_set_nugget must be called first");
+  CU(cudaSetDevice(h->device));
+  return launch_likelihood(h, static_cast<cudaStream_t>(stream));
+}
+
+int mra_fetch_likelihood(mra_handle* h, void* stream, double out[2]) {
+  if (!h || !out) return MRA_ERR_ARG;
+  if (!h->lik_done) return fail(h, MRA_ERR_STATE, "no likelihood pass has been run");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaMemcpyAsync(out, h->ws + h->lay.out, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  return check_status(h, st);
+}
+
+int mra_run_likelihood(mra_handle* h, void* stream, double out[2]) {
+  int rc = mra_run_likelihood_async(h, stream);
+  if (rc) return rc;
+  return mra_fetch_likelihood(h, stream, out);
+}
+
+int mra_run_predict_dev(mra_handle* h, void* stream, double* dev_mean, double* dev_sd) {
+  if (!h) return MRA_ERR_ARG;
+  if (!h->lik_done) return fail(h, MRA_ERR_STATE, "mra_run_likelihood must be called first");
+  if (!h->want_predict) return fail(h, MRA_ERR_STATE, "mra_plan was called with want_predict = 0");
+  CU(cudaSetDevice(h->device));
+  return launch_predict(h, static_cast<cudaStream_t>(stream), dev_mean, dev_sd);
+}
+
+int mra_run_predict(mra_handle* h, void* stream, double* mean, double* sd) {
+  if (!h || !mean || !sd) return MRA_ERR_ARG;
+  int rc = mra_run_predict_dev(h, stream, nullptr, nullptr);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaMemcpyAsync(mean, h->ws + h->lay.out_mean, sizeof(double) * h->N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(sd, h->ws + h->lay.out_sd, sizeof(double) * h->N, cudaMemcpyDeviceToHost, st));
+  return check_status(h, st);
+}
+
+int mra_last_launches(const mra_handle* h, int64_t* n) {
+  if (!h || !n) return MRA_ERR_ARG;
+  *n = h->launches;
+  return MRA_OK;
+}
+
+int mra_last_flops(const mra_handle* h, double* likelihood_flops, double* predict_flops) {
+  if (!h) return MRA_ERR_ARG;
+  if (likelihood_flops) *likelihood_flops = h->flops_lik;
+  if (predict_flops) *predict_flops = h->flops_pred;
+  return MRA_OK;
+}
+
+int64_t mra_debug_fetch(mra_handle* h, const char* what, int node, double* out, int64_t max_doubles) {
+  if (!h || !what || !out) return MRA_ERR_ARG;
+  if (!h->uploaded) return fail(h, MRA_ERR_STATE, "nothing on the device yet");
+  const Layout& L = h->lay;
+  const std::string w(what);
+  size_t off = 0;
+  int64_t cnt = 0;
+  const int r = h->r;
+  if (w == "V") {
+    off = L.V;
+    cnt = h->N * h->ldv;
+  } else if (w == "dnode") {
+    off = L.dnode;
+    cnt = h->n_nodes;
+  } else if (w == "mean") {
+    off = L.mean;
+    cnt = h->N;
+  } else if (w == "var") {
+    off = L.var;
+    cnt = h->N;
+  } else {
+    if (node < 0 || node >= h->n_nodes) return fail(h, MRA_ERR_ARG, "node out of range");
+    const NodeDev& d = h->nodes[node];
+    if (w == "A") { off = L.A + 8 * d.a_off; cnt = (int64_t)((d.level + 1) * r + 1) * d.lda; }
+    else if (w == "GT") { off = L.GT + 8 * d.gt_off; cnt = (int64_t)d.W * r; }
+    else if (w == "LPINV") { off = L.LPINV + 8 * d.lpinv_off; cnt = (int64_t)r * r; }
+    else if (w == "LINV") { off = L.LINV + 8 * d.linv_off; cnt = (int64_t)r * r; }
+    else if (w == "VK") { off = L.VK + 8 * d.vk_off; cnt = (int64_t)r * d.level * r; }
+    else if (w == "S") { off = L.S + 8 * d.s_off; cnt = (int64_t)d.n_obs * d.ldo; }
+    else if (w == "UT") { off = L.UT + 8 * d.ut_off; cnt = (int64_t)d.W * d.ldo; }
+    else if (w == "QT") { off = L.QT + 8 * d.qt_off; cnt = (int64_t)d.row_count * d.ldo; }
+    else return fail(h, MRA_ERR_ARG, "unknown buffer name");
+    if (d.kind == KIND_INTERNAL && (w == "S" || w == "UT" || w == "QT")) return fail(h, MRA_ERR_ARG, "leaf buffer of an internal node");
+    if (d.kind != KIND_INTERNAL && !(w == "S" || w == "UT" || w == "QT")) return fail(h, MRA_ERR_ARG, "internal buffer of a leaf");
+  }
+  cnt = std::min(cnt, max_doubles);
+  if (cudaSetDevice(h->device) != cudaSuccess) return MRA_ERR_CUDA;
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail(h, MRA_ERR_CUDA, "device synchronize failed");
+  if (cudaMemcpy(out, h->ws + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(h, MRA_ERR_CUDA, "debug copy failed");
+  return cnt;
+}
+
+}  // extern "C"

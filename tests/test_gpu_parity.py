@@ -1,0 +1,59 @@
+"""Parity of the CUDA path (through the C ABI, via pymra_b200.MRATree) against the golden vectors
+recorded from the unmodified reference and against the oracle on the same seeded inputs.
+
+Tolerances: north_star asks 1e-9 relative (likelihood / predictions / sd).  Where the reference's own
+FP64 noise is above that (ill-conditioned fixtures) the bound is a multiple of the
+measured oracle-vs-reference gap, i.e. "within the reference's own noise floor".
+"""
+import numpy as np
+import pytest
+
+from _util import errs, golden_names, load_golden, oracle_for, tree_for
+
+pytestmark = pytest.mark.gpu
+
+LIK_TOL, MEAN_TOL, SD_TOL = 1e-9, 1e-9, 1e-9
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_reference_and_oracle(name):
+    g = load_golden(name)
+    o = oracle_for(g)
+    fl, fm, fs = errs(o["lik"], o["mean"], o["sd"], g)          # reference's own noise floor
+    t = tree_for(g)
+    assert t.M == int(g["M_eff"]) and t.J == int(g["J_eff"])
+    lik = float(t.getLikelihood())
+    mean, sd = t.predict()
+    assert mean.shape == (len(g["locs"]), 1) and isinstance(mean, np.matrix) and sd.shape == (len(g["locs"]),)
+    scale = max(1.0, float(np.max(np.abs(g["mean"]))))
+    for ref in (g, o):
+        rl, em, es = errs(lik, mean, sd, ref)
+        assert rl <= max(LIK_TOL, 20 * fl), ("lik", rl, fl)
+        assert em <= max(MEAN_TOL * scale, 20 * fm), ("mean", em, fm)
+        assert es <= max(SD_TOL, 20 * fs), ("sd", es, fs)
+    assert np.array_equal(t.root.kInds, g["root_kinds"])
+
+
+def test_refit_equals_fresh_construction():
+    import pymra_b200.MRATools as mt
+    g = load_golden("g64_m3_exp")
+    t = tree_for(g)
+    l0 = float(t.getLikelihood())
+    l1 = float(t.refit(cov=lambda a, b: mt.ExpCovFun(a, b, l=0.45)))
+    assert l1 != l0
+    l2 = float(t.refit(cov=lambda a, b: mt.ExpCovFun(a, b, l=float(g["l"]))))
+    assert l2 == l0                                       # deterministic: bitwise repeatable
+    m, s = t.predict()
+    m2, s2 = t.predict()
+    assert np.array_equal(m, m2) and np.array_equal(s, s2)
+
+
+def test_non_spd_is_reported():
+    import pymra_b200.MRATools as mt
+    from pymra_b200 import _ffi
+    from pymra_b200.MRATree import MRATree
+    locs = np.repeat(mt.genLocations2d(12), 2, axis=0)     # duplicated locations -> singular knots
+    obs = np.zeros((len(locs), 1))
+    np.random.seed(0)
+    with pytest.raises(_ffi.MraError):
+        MRATree(locs, 200 if False else 16, lambda a, b: mt.ExpCovFun(a, b, l=0.5), obs, 1e-2, M=1)
