@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the MRA hot path (BASELINE.json: getLikelihood() evals/s and predict() locations/s
+at n = 4M) -- prints ONE JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full pass of the hot path over the workload: prior pass + leaf terms + upward pass
+(the likelihood) + downward pass (predictive mean and sd at every location), i.e. what one
+`MRATree(...)` construction computes in the reference.
+  value : steps/s with the inputs already resident in HBM (device-timed, CUDA events).
+  e2e   : the same through the reference-facing API `MRATree(locs, r, cov, obs, R, M=..)` +
+          getLikelihood() + predict() with HOST numpy buffers: host tree construction, H2D, compute,
+          D2H of mean/sd all inside the timed region.
+  roofline : the dominant kernel family (by device time), algorithmic FP64 flop / CUDA-event time,
+          against a cuBLAS DGEMM peak measured in this run (MEASURED_PEAKS.json has no FP64 entry).
+  cpu_baseline : the oracle port (oracle/mra_oracle.py, NumPy/LAPACK on the host cores) on a bounded
+          sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (grid side, r0, M requested, family, l, sig, R, frac_obs)
+    "cfg5": (2000, 64, 10, "matern32", 0.3, 1.0, 1e-2, 0.4),   # BASELINE.json configs[4] (metric config)
+    "cfg3": (1000, 32, 8, "matern32", 0.3, 1.0, 1e-2, 0.4),    # configs[2]
+    "cfg4": (500, 16, 7, "matern32", 0.3, 1.0, 1e-2, 0.4),     # configs[3] (one evaluation)
+    "tiny": (250, 64, 10, "matern32", 0.3, 1.0, 1e-2, 0.4),
+}
+SAMPLE_GRID = 250   # cpu baseline sample: one level-3 subtree of cfg5 (same r0, same leaf sizes)
+
+
+def make_inputs(n, frac_obs, seed=3):
+    import pymra_b200.MRATools as mt
+    locs = mt.genLocations2d(n)
+    N = len(locs)
+    rng = np.random.RandomState(seed)
+    f = np.sin(5.0 * locs[:, 0]) * np.cos(3.0 * locs[:, 1]) + 0.5 * np.sin(11.0 * locs[:, 0] * locs[:, 1])
+    y = f.reshape(-1, 1) + 0.3 * rng.normal(size=(N, 1))
+    obs = np.full((N, 1), np.nan)
+    sel = np.sort(rng.choice(N, int(frac_obs * N), replace=False))
+    obs[sel] = y[sel]
+    return locs, obs
+
+
+def make_cov(family, l, sig):
+    import pymra_b200.MRATools as mt
+    if family == "exp":
+        return lambda a, b: mt.ExpCovFun(a, b, l=l)
+    return lambda a, b: mt.Matern32(a, b, l=l, sig=sig)
+
+
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            # under load = samples in the upper half of the observed range
+            hi = [s for s in sm if s >= 0.5 * max(sm)]
+            out.update(sm_mhz=float(np.median(hi)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def dgemm_peak_tflops(torch, n=6144):
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(4):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / best * 1e-9
+
+
+def cpu_baseline(r, M, family, l, sig, R, frac_obs, n_full, steps=1, warmup=0):
+    """Oracle port on a bounded sample; returns (evals/s at the full size, description, cores, s/step)."""
+    from oracle.mra_oracle import mra_oracle
+    locs, obs = make_inputs(SAMPLE_GRID, frac_obs, seed=4)
+    times = []
+    for it in range(warmup + steps):
+        np.random.seed(5)
+        t0 = time.time()
+        mra_oracle(locs, r, family, l, sig, obs, R, M=M)
+        dt = time.time() - t0
+        if it >= warmup:
+            times.append(dt)
+    per = float(np.mean(times))
+    locs_per_s = len(locs) / per
+    return locs_per_s / n_full, locs_per_s, per
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n, r, M, family, l, sig, R, frac = WORKLOADS[args.workload]
+    N = n * n
+    t0 = time.time()
+    evals, locs_s, per = cpu_baseline(r, M, family, l, sig, R, frac, N, steps=args.steps, warmup=args.warmup)
+    cores = os.cpu_count()
+    sample = ("oracle/mra_oracle.py (NumPy/LAPACK restatement of pyMRA, gc.collect not called) on a %dx%d grid, "
+              "r0=%d: one level-3 subtree of the workload, same leaf sizes; %.0f locs/s scaled by 1/N to evals/s "
+              "(optimistic for the CPU: the full tree is 3 levels deeper)" % (SAMPLE_GRID, SAMPLE_GRID, r, locs_s))
+    line = {"impl": "reference", "metric": "getLikelihood() evals/sec and predict() locations/sec at n=4M",
+            "value": evals, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "grid": [n, n], "n_locs": N, "r0": r, "M_requested": M,
+                       "cov": family, "l": l, "R": R, "frac_obs": frac},
+            "predict_locations_per_s": locs_s,
+            "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": evals, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from pymra_b200.covariance import introspect
+    from pymra_b200.MRATree import MRATree, resolve_params
+    from pymra_b200.session import DeviceSession
+    from pymra_b200.structure import build_structure
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, r, Mreq, family, l, sig, R, frac = WORKLOADS[args.workload]
+    N = n * n
+    locs, obs = make_inputs(n, frac)
+    cov = make_cov(family, l, sig)
+    desc = introspect(cov, 2)
+    M, J, critDepth, _ = resolve_params(N, 2, r, Mreq, -1, -1)
+
+    if world > 1:
+        raise SystemExit("bench.py: multi-GPU subtree sharding is not wired in yet")
+
+    # ---- device-resident timing
+    np.random.seed(5)
+    t0 = time.time()
+    st = build_structure(locs, r, M, J, critDepth)
+    t_struct = time.time() - t0
+    sess = DeviceSession(st, locs, obs, want_predict=True)
+    sess.set_params(desc, R)
+    mean_t = torch.empty(N, dtype=torch.float64, device="cuda")
+    sd_t = torch.empty(N, dtype=torch.float64, device="cuda")
+
+    def step():
+        sess.likelihood_async()
+        sess.predict_dev(mean_t, sd_t)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sess.profile_enable(True)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    lik_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for i in range(args.steps):
+        ev[i][0].record()
+        sess.likelihood_async()
+        lik_ev[i].record()
+        sess.predict_dev(mean_t, sd_t)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    launches = sess.launches()
+    prof = sess.profile_read()
+    sess.profile_enable(False)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    lik_ms = [ev[i][0].elapsed_time(lik_ev[i]) for i in range(args.steps)]
+    total_ms = float(sum(step_ms))
+    d, u = sess.fetch_likelihood()
+    value = args.steps / (total_ms * 1e-3)
+    f_lik, f_pred = sess.flops()
+
+    # ---- end to end through the reference-facing API (host buffers in, host results out)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t_e2e = []
+    lik_e2e = None
+    for i in range(1 + e2e_steps):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        tree = MRATree(locs, r, cov, obs, R, M=Mreq)
+        lik_e2e = float(np.asarray(tree.getLikelihood()).ravel()[0])
+        mean_h, sd_h = tree.predict()
+        torch.cuda.synchronize()
+        if i > 0:
+            t_e2e.append(time.time() - t0)
+        del tree
+    e2e_value = 1.0 / float(np.mean(t_e2e))
+    clocks = sampler.stop()
+    h2d = N * 8 * 3 + sess.h2d_structure_bytes
+    d2h = N * 16 + 16
+
+    # ---- roofline of the dominant kernel family
+    peak = dgemm_peak_tflops(torch)
+    kern = {}
+    for name, p in prof.items():
+        if p["launches"] == 0:
+            continue
+        ms = p["ms"] / args.steps
+        kern[name] = {"ms_per_step": ms, "launches_per_step": p["launches"] / args.steps,
+                      "tflops": p["flops"] / (ms * 1e-3) * 1e-12 if ms > 0 else 0.0,
+                      "gbs": p["bytes"] / (ms * 1e-3) * 1e-9 if ms > 0 else 0.0}
+    top = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    roofline = {"kernel": top, "bound": "tensor", "achieved": kern[top]["tflops"], "peak": peak,
+                "unit": "TFLOP/s", "frac": kern[top]["tflops"] / peak, "traffic": None,
+                "peak_source": "cuBLAS DGEMM (torch.matmul f64, n=6144) measured in this run; "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "share_of_step": kern[top]["ms_per_step"] / (total_ms / args.steps),
+                "whole_step_tflops": (f_lik + f_pred) / (total_ms / args.steps * 1e-3) * 1e-12}
+
+    # ---- CPU baseline (rank 0, bounded sample)
+    cb = None
+    if not args.no_cpu_baseline:
+        evals, locs_s, per = cpu_baseline(r, Mreq, family, l, sig, R, frac, N)
+        cb = {"value": evals, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+              "sample": "oracle/mra_oracle.py on a %dx%d grid, r0=%d (one level-3 subtree of the workload, same leaf "
+                        "sizes): %.1f s, %.0f locs/s, scaled by 1/N" % (SAMPLE_GRID, SAMPLE_GRID, r, per, locs_s)}
+
+    line = {"metric": "getLikelihood() evals/sec and predict() locations/sec at n=4M",
+            "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "grid": [n, n], "n_locs": N, "r0": r, "M_requested": Mreq,
+                       "M_effective": M, "J": J, "cov": family, "l": l, "sig": sig, "R": R, "frac_obs": frac,
+                       "nodes": int(st.n_nodes), "l2_policy": "inputs larger than L2 (basis stack %.1f GB)" % (
+                           N * max(st.depth, 1) * r * 8 / 1e9),
+                       "step": "likelihood pass + predict pass on a frozen tree, inputs resident in HBM"},
+            "predict_locations_per_s": value * N,
+            "likelihood_only_evals_per_s": args.steps / (sum(lik_ms) * 1e-3),
+            "likelihood": d + u,
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "predict_locations_per_s": e2e_value * N, "host_structure_s": t_struct,
+                    "what": "MRATree(locs, r, cov, obs, R, M) + getLikelihood() + predict(), host numpy in/out, "
+                            "fresh knot draw per construction (reference RNG semantics)",
+                    "likelihood": lik_e2e},
+            "gpu_launches": int(launches * args.steps),
+            "roofline": roofline, "kernels": kern, "cpu_baseline": cb, "clocks": clocks,
+            "algorithmic_flops": {"likelihood": f_lik, "predict": f_pred},
+            "workspace_gb": sess.workspace_bytes / 1e9}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import __graft_entry__ as ge
+    if rank == 0 or not os.path.exists(ge.LIB):
+        pass   # the library is built by __graft_entry__.build(); bench never compiles in the timed path
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

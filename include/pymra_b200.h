@@ -110,6 +110,12 @@ int mra_fetch_likelihood(mra_handle *h, void *stream, double out[2]);
 int mra_last_launches(const mra_handle *h, int64_t *n);
 int mra_last_flops(const mra_handle *h, double *likelihood_flops, double *predict_flops);
 
+/* Per-kernel timing for bench.py's roofline block: when enabled every kernel launch is bracketed
+ * by CUDA events on the launching stream.  mra_profile_read synchronises and writes one line per
+ * kernel family: "name total_ms launches algorithmic_flops_per_pass algorithmic_bytes_per_pass". */
+int mra_profile_enable(mra_handle *h, int on);
+int mra_profile_read(mra_handle *h, char *buf, size_t buflen);
+
 /* Test hook: copies an internal device buffer to the host.
  * what: "V" (N x ldv, node ignored), "A", "GT", "LPINV", "LINV", "VK" (per node), "dnode" (all nodes).
  * Returns the number of doubles written (<= max_doubles) or a negative status. */

@@ -8,23 +8,15 @@ Same constructor signature and semantics as the reference class; the work the re
     pass for the likelihood, downward pass for predictions.
 PyTorch only supplies the device arena and the stream.  There is no CPU fallback.
 """
-import ctypes as C
 import logging
 
 import numpy as np
 
-from . import _ffi
 from .covariance import introspect
+from .session import DeviceSession
 from .structure import build_structure
 
 logger = logging.getLogger("pymra_b200.MRATree")
-
-
-def _torch():
-    import torch
-    if not torch.cuda.is_available():
-        raise RuntimeError("pymra_b200.MRATree needs a CUDA device (B200); there is no CPU fallback")
-    return torch
 
 
 def resolve_params(N, d, r, M, J, critDepth):
@@ -76,7 +68,6 @@ class _Root(object):
 class MRATree(object):
 
     def __init__(self, locs, r, cov, obs, R, M=-1, J=-1, critDepth=-1, verbose=True, device=None):
-        torch = _torch()
         self.locs = locs
         self.d = np.shape(self.locs)[1]
         N = len(locs)
@@ -101,93 +92,25 @@ class MRATree(object):
 
         locs_c = np.ascontiguousarray(locs, dtype=np.float64).reshape(N, self.d)
         self._structure = build_structure(locs_c, r, M, J, critDepth)
-
-        self._dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        self._lib = _ffi.lib()
-        self._h = C.c_void_p()
-        st = self._lib.mra_create(C.byref(self._h), self._dev.index)
-        if st != 0:
-            raise _ffi.MraError(st, "mra_create failed (no usable CUDA device?)")
-        self._obs_c = np.ascontiguousarray(obs_arr.reshape(N))
-        self._locs_c = locs_c
-        self._set_structure()
-        nbytes = C.c_size_t()
-        self._check(self._lib.mra_plan(self._h, self._ptr(self._obs_c), 1, C.byref(nbytes)))
-        self._ws = torch.empty(int(nbytes.value) + 256, dtype=torch.uint8, device=self._dev)
-        base = self._ws.data_ptr()
-        aligned = (base + 255) // 256 * 256
-        self._check(self._lib.mra_bind_workspace(self._h, C.c_void_p(aligned), C.c_size_t(int(nbytes.value))))
-        self._check(self._lib.mra_upload_data(self._h, self._ptr(self._locs_c), self._ptr(self._obs_c), self._stream()))
+        self._session = DeviceSession(self._structure, locs_c, obs_arr, want_predict=True, device=device)
         self._mom = None
         self._evaluate()
         self.root = _Root(self)
 
     # ---- plumbing
-    @staticmethod
-    def _ptr(a):
-        return a.ctypes.data_as(C.POINTER(C.c_double))
-
-    def _stream(self):
-        import torch
-        return C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
-
-    def _check(self, status):
-        _ffi.check(self._h, status)
-
-    def _set_structure(self):
-        s = self._structure
-        keep = dict(
-            node_level=np.ascontiguousarray(s.node_level, dtype=np.int32),
-            node_parent=np.ascontiguousarray(s.node_parent, dtype=np.int32),
-            node_kind=np.ascontiguousarray(s.node_kind, dtype=np.int32),
-            node_row_start=np.ascontiguousarray(s.node_row_start, dtype=np.int64),
-            node_row_count=np.ascontiguousarray(s.node_row_count, dtype=np.int64),
-            node_child_start=np.ascontiguousarray(s.node_child_start, dtype=np.int32),
-            node_child_count=np.ascontiguousarray(s.node_child_count, dtype=np.int32),
-            node_knot_off=np.ascontiguousarray(s.node_knot_off, dtype=np.int64),
-            knot_rows=np.ascontiguousarray(s.knot_rows, dtype=np.int64),
-            level_off=np.ascontiguousarray(s.level_off, dtype=np.int32),
-            perm=np.ascontiguousarray(s.perm, dtype=np.int64))
-        ms = _ffi.MraStructure()
-        ms.n_locs, ms.dim, ms.r, ms.depth, ms.n_nodes = s.N, s.d, s.r, s.depth, s.n_nodes
-        ms.n_knot_rows = len(keep["knot_rows"])
-        for name, arr in keep.items():
-            ctype = C.c_int32 if arr.dtype == np.int32 else C.c_int64
-            setattr(ms, name, arr.ctypes.data_as(C.POINTER(ctype)))
-        self._check(self._lib.mra_set_structure(self._h, C.byref(ms)))
-
     def _evaluate(self):
-        self._check(self._lib.mra_set_cov(self._h, self._cov.family, self._cov.l, self._cov.sig))
-        self._check(self._lib.mra_set_nugget(self._h, self._R))
-        out = (C.c_double * 2)()
-        self._check(self._lib.mra_run_likelihood(self._h, self._stream(), out))
-        self._d, self._u = float(out[0]), float(out[1])
+        self._session.set_params(self._cov, self._R)
+        self._d, self._u = self._session.likelihood()
         self._mom = None
 
     def _moments(self):
         if self._mom is None:
-            mean = np.empty(self._N)
-            sd = np.empty(self._N)
-            self._check(self._lib.mra_run_predict(self._h, self._stream(), self._ptr(mean), self._ptr(sd)))
+            mean, sd = self._session.predict()
             self._mom = (np.matrix(mean.reshape(-1, 1)), sd * sd, sd)
         return self._mom
 
     def _debug_fetch(self, what, node=0, count=None):
-        if count is None:
-            count = 1 << 24
-        buf = np.empty(count)
-        n = self._lib.mra_debug_fetch(self._h, what.encode(), int(node), self._ptr(buf), C.c_int64(count))
-        if n < 0:
-            self._check(int(n))
-        return buf[:n].copy()
-
-    def __del__(self):
-        try:
-            if getattr(self, "_h", None):
-                self._lib.mra_destroy(self._h)
-                self._h = None
-        except Exception:
-            pass
+        return self._session.debug_fetch(what, node, count)
 
     # ---- reference API
     def getLikelihood(self):

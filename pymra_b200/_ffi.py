@@ -46,6 +46,8 @@ SIGNATURES = {
     "mra_fetch_likelihood": (C.c_int, [C.c_void_p, C.c_void_p, _pd]),
     "mra_last_launches": (C.c_int, [C.c_void_p, _p64]),
     "mra_last_flops": (C.c_int, [C.c_void_p, _pd, _pd]),
+    "mra_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "mra_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "mra_debug_fetch": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int, _pd, C.c_int64]),
 }
 

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -65,6 +66,16 @@ struct mra_handle {
   bool cov_set = false, R_set = false;
   int64_t launches = 0;
   double flops_lik = 0, flops_pred = 0;
+  // per-kernel profiling (CUDA events on the launching stream)
+  bool profiling = false;
+  struct ProfRec { int kid; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> event_pool;
+  std::map<std::string, int> kid_of;
+  std::vector<std::string> kname;
+  std::vector<double> kflops, kbytes;   // algorithmic work per launch-group, accumulated at plan time
+  std::vector<double> kms;
+  std::vector<int64_t> klaunch;
 };
 
 namespace {
@@ -141,6 +152,61 @@ int configure_kernels(mra_handle* h) {
   return MRA_OK;
 }
 
+int kid(mra_handle* h, const std::string& name) {
+  auto it = h->kid_of.find(name);
+  if (it != h->kid_of.end()) return it->second;
+  int id = (int)h->kname.size();
+  h->kid_of[name] = id;
+  h->kname.push_back(name);
+  h->kflops.push_back(0.0);
+  h->kbytes.push_back(0.0);
+  h->kms.push_back(0.0);
+  h->klaunch.push_back(0);
+  return id;
+}
+
+void add_work(mra_handle* h, const std::string& name, double flops, double bytes) {
+  int id = kid(h, name);
+  h->kflops[id] += flops;
+  h->kbytes[id] += bytes;
+}
+
+cudaEvent_t get_event(mra_handle* h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ProfScope {
+  mra_handle* h;
+  cudaStream_t st;
+  mra_handle::ProfRec rec;
+  bool on;
+  ProfScope(mra_handle* h_, cudaStream_t st_, const char* name) : h(h_), st(st_), on(h_->profiling) {
+    ++h->launches;
+    if (!on) return;
+    rec.kid = kid(h, name);
+    rec.e0 = get_event(h);
+    rec.e1 = get_event(h);
+    cudaEventRecord(rec.e0, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(rec.e1, st);
+    h->prof_recs.push_back(rec);
+  }
+};
+#define LAUNCH(name, ...)            \
+  do {                               \
+    ProfScope ps_(h, st, name);      \
+    __VA_ARGS__;                     \
+  } while (0)
+
 int check_status(mra_handle* h, cudaStream_t st) {
   int flag = 0;
   CU(cudaMemcpyAsync(&flag, at<int>(h, h->lay.status), sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -162,12 +228,10 @@ int launch_likelihood(mra_handle* h, cudaStream_t st) {
     const int nn = (int)h->internal_at[m].size();
     if (!nn) continue;
     const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
-    k_knot_factor<<<nn, NT, smem_knot(r), st>>>(c, list);
-    ++h->launches;
+    LAUNCH("knot_factor", k_knot_factor<<<nn, NT, smem_knot(r), st>>>(c, list));
     const int ntile = (int)h->tiles_at[m].size();
     const int4* tiles = reinterpret_cast<const int4*>(h->ws + L.tiles + h->tiles_off[m]);
-    k_prior_tiles<<<ntile, NT, smem_prior(r), st>>>(c, tiles, m);
-    ++h->launches;
+    LAUNCH("prior_tiles", k_prior_tiles<<<ntile, NT, smem_prior(r), st>>>(c, tiles, m));
   }
   // ---- leaves
   const int nleaf = (int)h->leaves.size();
@@ -175,16 +239,13 @@ int launch_likelihood(mra_handle* h, cudaStream_t st) {
   if (nleaf && h->max_leaf_obs > 0) {
     const int nbo = (h->max_leaf_obs + TB - 1) / TB;
     dim3 g1(nleaf, nbo * (nbo + 1) / 2);
-    k_leaf_gram<<<g1, NT, 0, st>>>(c, leaf_list, 0);
-    ++h->launches;
+    LAUNCH("leaf_gram", k_leaf_gram<<<g1, NT, 0, st>>>(c, leaf_list, 0));
     for (int p = 0; p < nbo; ++p) {
       dim3 g2(nleaf, nbo - p);
-      k_leaf_chol_step<<<g2, NT, smem_chol(), st>>>(c, leaf_list, p);
-      ++h->launches;
+      LAUNCH("leaf_chol", k_leaf_chol_step<<<g2, NT, smem_chol(), st>>>(c, leaf_list, p));
     }
     dim3 g3(nleaf, (h->max_leaf_W + TB - 1) / TB);
-    k_leaf_solve<<<g3, NT, smem_solve(), st>>>(c, leaf_list, 0);
-    ++h->launches;
+    LAUNCH("leaf_solve", k_leaf_solve<<<g3, NT, smem_solve(), st>>>(c, leaf_list, 0));
   }
   // ---- upward
   for (int m = (int)h->internal_at.size() - 1; m >= 0; --m) {
@@ -193,14 +254,11 @@ int launch_likelihood(mra_handle* h, cudaStream_t st) {
     const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
     const int W = (m + 1) * r + 1, nb = (W + TB - 1) / TB;
     dim3 ga(nn, nb * (nb + 1) / 2);
-    k_assemble_A<<<ga, NT, 0, st>>>(c, list);
-    ++h->launches;
+    LAUNCH("assemble_A", k_assemble_A<<<ga, NT, 0, st>>>(c, list));
     dim3 gf(nn, (m * r + 1 + TB - 1) / TB);
-    k_node_factor<<<gf, NT, smem_factor(r), st>>>(c, list);
-    ++h->launches;
+    LAUNCH("node_factor", k_node_factor<<<gf, NT, smem_factor(r), st>>>(c, list));
   }
-  k_finalize<<<1, NT, 0, st>>>(c, at<double>(h, L.out));
-  ++h->launches;
+  LAUNCH("finalize", k_finalize<<<1, NT, 0, st>>>(c, at<double>(h, L.out)));
   CU(cudaGetLastError());
   h->lik_done = true;
   h->pred_done = false;
@@ -214,34 +272,28 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
   if (!h->pred_done) {
     const int nleaf = (int)h->leaves.size();
     const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off);
-    k_resid_var<<<nleaf, 256, 0, st>>>(c, leaf_list);
-    ++h->launches;
+    LAUNCH("resid_var", k_resid_var<<<nleaf, 256, 0, st>>>(c, leaf_list));
     if (h->max_leaf_obs > 0) {
       const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
       dim3 g1(nleaf, nbr * nbo);
-      k_leaf_gram<<<g1, NT, 0, st>>>(c, leaf_list, 1);
-      ++h->launches;
+      LAUNCH("leaf_gram_T", k_leaf_gram<<<g1, NT, 0, st>>>(c, leaf_list, 1));
       dim3 g2(nleaf, nbr);
-      k_leaf_solve<<<g2, NT, smem_solve(), st>>>(c, leaf_list, 1);
-      ++h->launches;
+      LAUNCH("leaf_solve_Q", k_leaf_solve<<<g2, NT, smem_solve(), st>>>(c, leaf_list, 1));
       dim3 g3(nleaf, nbr * ((h->max_leaf_W + TB - 1) / TB));
-      k_leaf_apply<<<g3, NT, 0, st>>>(c, leaf_list);
-      ++h->launches;
+      LAUNCH("leaf_apply", k_leaf_apply<<<g3, NT, 0, st>>>(c, leaf_list));
     }
     for (int m = (int)h->internal_at.size() - 1; m >= 0; --m) {
       const int ntile = (int)h->tiles_at[m].size();
       if (!ntile) continue;
       const int4* tiles = reinterpret_cast<const int4*>(h->ws + L.tiles + h->tiles_off[m]);
-      k_predict_level<<<ntile, NT, smem_predict(r), st>>>(c, tiles, m);
-      ++h->launches;
+      LAUNCH("predict_level", k_predict_level<<<ntile, NT, smem_predict(r), st>>>(c, tiles, m));
     }
     h->pred_done = true;   // V now holds the posterior-updated basis; results stay cached in mean/var
   }
   const int N = (int)h->N;
-  k_unpermute<<<(N + 255) / 256, 256, 0, st>>>(c.mean, c.var, at<int>(h, L.perm), N,
-                                               dev_mean ? dev_mean : at<double>(h, L.out_mean),
-                                               dev_sd ? dev_sd : at<double>(h, L.out_sd));
-  ++h->launches;
+  LAUNCH("unpermute", k_unpermute<<<(N + 255) / 256, 256, 0, st>>>(c.mean, c.var, at<int>(h, L.perm), N,
+                                                                    dev_mean ? dev_mean : at<double>(h, L.out_mean),
+                                                                    dev_sd ? dev_sd : at<double>(h, L.out_sd)));
   CU(cudaGetLastError());
   return MRA_OK;
 }
@@ -349,7 +401,8 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
             linv_off = 0;
   h->max_leaf_obs = h->max_leaf_rows = 0;
   h->max_leaf_W = 1;
-  double f_lik = 0, f_pred = 0;
+  for (auto& f : h->kflops) f = 0.0;
+  for (auto& f : h->kbytes) f = 0.0;
   for (int n = 0; n < nn; ++n) {
     NodeDev& d = h->nodes[n];
     d.level = h->level[n];
@@ -375,12 +428,16 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       linv_off += (long long)r * r;
       d.vk_off = vk_off;
       vk_off += (long long)r * d.level * r;
-      const double nr = (double)d.row_count;
-      f_lik += 2.0 * r * r * Kv + r * (double)r * r / 3.0;           // knot covariance + factor
-      f_lik += 2.0 * nr * r * Kv + nr * r * (double)r;              // prior rows + whitening
-      f_lik += (double)r * r * r / 3.0 + 2.0 * r * r * Kv / 1.0;    // node factor + G
-      f_lik += (double)(Kv + 1) * (Kv + 1) * r;                     // Schur complement (symmetric half)
-      f_pred += nr * r * (double)r + 2.0 * nr * r * Kv;             // t and basis update
+      const double nr = (double)d.row_count, rr = (double)r;
+      const double Waf = Kv + rr + 1;
+      add_work(h, "knot_factor", rr * rr * Kv + 2.0 * rr * rr * rr / 3.0, 8.0 * (2.0 * rr * Kv + rr * rr));
+      add_work(h, "prior_tiles", 2.0 * nr * rr * Kv + nr * rr * rr, 8.0 * nr * (Kv + rr + 2));
+      double fa = 0;     // assemble: symmetric half of W x W, K = n_obs (leaf child) or r (internal child)
+      for (int ch = d.child_start; ch < d.child_start + d.child_count; ++ch)
+        if (h->kind[ch] == KIND_INTERNAL) fa += Waf * Waf * rr;
+      add_work(h, "assemble_A", fa, 8.0 * Waf * Waf);
+      add_work(h, "node_factor", 2.0 * rr * rr * rr / 3.0 + (Kv + 1) * rr * rr, 8.0 * (rr * rr + 2 * (Kv + 1) * rr));
+      add_work(h, "predict_level", nr * rr * rr + 2.0 * nr * rr * Kv + 4.0 * nr * rr, 8.0 * nr * (2 * Kv + rr + 4));
     } else {
       d.obs_off = (int)h->obs_rows.size();
       if (d.kind == KIND_LEAF) {
@@ -403,14 +460,28 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       h->max_leaf_obs = std::max(h->max_leaf_obs, d.n_obs);
       h->max_leaf_rows = std::max(h->max_leaf_rows, d.row_count);
       if (d.n_obs > 0) h->max_leaf_W = std::max(h->max_leaf_W, d.W);
-      const double no = d.n_obs, nl = d.row_count;
-      f_lik += no * no * Kv + no * no * no / 3.0 + no * no * (Kv + 1) + no * (Kv + 1) * (Kv + 1);
-      f_pred += 2.0 * no * nl * Kv + no * no * nl + 2.0 * nl * no * (Kv + 1);
+      const double no = d.n_obs, nl = d.row_count, W = Kv + 1;
+      add_work(h, "leaf_gram", no * no * Kv, 8.0 * (no * Kv + no * no / 2));
+      add_work(h, "leaf_chol", no * no * no / 3.0, 8.0 * no * no);
+      add_work(h, "leaf_solve", no * no * W, 8.0 * (2 * no * W + no * no / 2));
+      add_work(h, "assemble_A", W * W * no, 8.0 * no * W);
+      if (d.kind == KIND_LEAF) {
+        add_work(h, "resid_var", 2.0 * nl * Kv, 8.0 * nl * (Kv + 2));
+        add_work(h, "leaf_gram_T", 2.0 * nl * no * Kv, 8.0 * ((nl + no) * Kv + nl * no));
+        add_work(h, "leaf_solve_Q", nl * no * no, 8.0 * (2 * nl * no + no * no / 2));
+        add_work(h, "leaf_apply", 2.0 * nl * no * W + 2.0 * nl * no, 8.0 * (nl * no + no * W + 2 * nl * Kv));
+      }
     }
   }
   h->n_obs_total = (int64_t)h->obs_rows.size();
-  h->flops_lik = f_lik;
-  h->flops_pred = f_pred;
+  add_work(h, "unpermute", 0.0, 8.0 * 4.0 * (double)h->N);
+  h->flops_lik = h->flops_pred = 0.0;
+  for (size_t i = 0; i < h->kname.size(); ++i) {
+    const std::string& nm = h->kname[i];
+    const bool pred = nm == "resid_var" || nm == "leaf_gram_T" || nm == "leaf_solve_Q" || nm == "leaf_apply" ||
+                      nm == "predict_level" || nm == "unpermute";
+    (pred ? h->flops_pred : h->flops_lik) += h->kflops[i];
+  }
   // ---- arena layout
   Arena ar;
   Layout& L = h->lay;
@@ -584,6 +655,44 @@ int mra_last_flops(const mra_handle* h, double* likelihood_flops, double* predic
   if (!h) return MRA_ERR_ARG;
   if (likelihood_flops) *likelihood_flops = h->flops_lik;
   if (predict_flops) *predict_flops = h->flops_pred;
+  return MRA_OK;
+}
+
+int mra_profile_enable(mra_handle* h, int on) {
+  if (!h) return MRA_ERR_ARG;
+  h->profiling = on != 0;
+  for (auto& r : h->prof_recs) {
+    h->event_pool.push_back(r.e0);
+    h->event_pool.push_back(r.e1);
+  }
+  h->prof_recs.clear();
+  for (auto& v : h->kms) v = 0.0;
+  for (auto& v : h->klaunch) v = 0;
+  return MRA_OK;
+}
+
+int mra_profile_read(mra_handle* h, char* buf, size_t buflen) {
+  if (!h || !buf || buflen == 0) return MRA_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  for (auto& r : h->prof_recs) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    h->kms[r.kid] += ms;
+    h->klaunch[r.kid] += 1;
+    h->event_pool.push_back(r.e0);
+    h->event_pool.push_back(r.e1);
+  }
+  h->prof_recs.clear();
+  std::string out;
+  char line[256];
+  for (size_t i = 0; i < h->kname.size(); ++i) {
+    snprintf(line, sizeof line, "%s %.6f %lld %.6e %.6e\n", h->kname[i].c_str(), h->kms[i],
+             (long long)h->klaunch[i], h->kflops[i], h->kbytes[i]);
+    out += line;
+  }
+  if (out.size() + 1 > buflen) return fail(h, MRA_ERR_NOMEM, "profile buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
   return MRA_OK;
 }
 

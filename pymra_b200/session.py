@@ -1,0 +1,149 @@
+"""DeviceSession: one device handle of the C ABI (include/pymra_b200.h) bound to one tree
+structure and one data set.  MRATree uses it for the reference-shaped API; bench.py uses it
+directly to time device-resident passes.  PyTorch supplies the arena and the stream only."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("pymra_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class DeviceSession(object):
+    def __init__(self, structure, locs, obs, want_predict=True, device=None):
+        torch = _torch()
+        self.structure = structure
+        self.N = structure.N
+        self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.lib = _ffi.lib()
+        self.h = C.c_void_p()
+        st = self.lib.mra_create(C.byref(self.h), self.dev.index)
+        if st != 0:
+            raise _ffi.MraError(st, "mra_create failed (no usable CUDA device?)")
+        self._set_structure()
+        obs_c = np.ascontiguousarray(np.asarray(obs, dtype=np.float64).reshape(self.N))
+        locs_c = np.ascontiguousarray(np.asarray(locs, dtype=np.float64).reshape(self.N, structure.d))
+        nbytes = C.c_size_t()
+        self.check(self.lib.mra_plan(self.h, _dptr(obs_c), 1 if want_predict else 0, C.byref(nbytes)))
+        self.workspace_bytes = int(nbytes.value)
+        self.ws = torch.empty(self.workspace_bytes + 256, dtype=torch.uint8, device=self.dev)
+        aligned = (self.ws.data_ptr() + 255) // 256 * 256
+        self.check(self.lib.mra_bind_workspace(self.h, C.c_void_p(aligned), C.c_size_t(self.workspace_bytes)))
+        self.upload(locs_c, obs_c)
+
+    # ---- plumbing
+    def check(self, status):
+        _ffi.check(self.h, status)
+
+    def stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _set_structure(self):
+        s = self.structure
+        keep = dict(
+            node_level=np.ascontiguousarray(s.node_level, dtype=np.int32),
+            node_parent=np.ascontiguousarray(s.node_parent, dtype=np.int32),
+            node_kind=np.ascontiguousarray(s.node_kind, dtype=np.int32),
+            node_row_start=np.ascontiguousarray(s.node_row_start, dtype=np.int64),
+            node_row_count=np.ascontiguousarray(s.node_row_count, dtype=np.int64),
+            node_child_start=np.ascontiguousarray(s.node_child_start, dtype=np.int32),
+            node_child_count=np.ascontiguousarray(s.node_child_count, dtype=np.int32),
+            node_knot_off=np.ascontiguousarray(s.node_knot_off, dtype=np.int64),
+            knot_rows=np.ascontiguousarray(s.knot_rows, dtype=np.int64),
+            level_off=np.ascontiguousarray(s.level_off, dtype=np.int32),
+            perm=np.ascontiguousarray(s.perm, dtype=np.int64))
+        ms = _ffi.MraStructure()
+        ms.n_locs, ms.dim, ms.r, ms.depth, ms.n_nodes = s.N, s.d, s.r, s.depth, s.n_nodes
+        ms.n_knot_rows = len(keep["knot_rows"])
+        for name, arr in keep.items():
+            ctype = C.c_int32 if arr.dtype == np.int32 else C.c_int64
+            setattr(ms, name, arr.ctypes.data_as(C.POINTER(ctype)))
+        self.check(self.lib.mra_set_structure(self.h, C.byref(ms)))
+        self.h2d_structure_bytes = sum(a.nbytes for a in keep.values())
+
+    # ---- data / parameters
+    def upload(self, locs_c, obs_c):
+        self.check(self.lib.mra_upload_data(self.h, _dptr(locs_c), _dptr(obs_c), self.stream()))
+
+    def set_params(self, cov, R):
+        self.check(self.lib.mra_set_cov(self.h, cov.family, cov.l, cov.sig))
+        self.check(self.lib.mra_set_nugget(self.h, float(R)))
+
+    # ---- passes
+    def likelihood(self):
+        out = (C.c_double * 2)()
+        self.check(self.lib.mra_run_likelihood(self.h, self.stream(), out))
+        return float(out[0]), float(out[1])
+
+    def likelihood_async(self):
+        self.check(self.lib.mra_run_likelihood_async(self.h, self.stream()))
+
+    def fetch_likelihood(self):
+        out = (C.c_double * 2)()
+        self.check(self.lib.mra_fetch_likelihood(self.h, self.stream(), out))
+        return float(out[0]), float(out[1])
+
+    def predict(self):
+        mean = np.empty(self.N)
+        sd = np.empty(self.N)
+        self.check(self.lib.mra_run_predict(self.h, self.stream(), _dptr(mean), _dptr(sd)))
+        return mean, sd
+
+    def predict_dev(self, mean_t=None, sd_t=None):
+        pm = C.c_void_p(mean_t.data_ptr()) if mean_t is not None else None
+        ps = C.c_void_p(sd_t.data_ptr()) if sd_t is not None else None
+        self.check(self.lib.mra_run_predict_dev(self.h, self.stream(), pm, ps))
+
+    # ---- counters
+    def launches(self):
+        n = C.c_int64()
+        self.check(self.lib.mra_last_launches(self.h, C.byref(n)))
+        return int(n.value)
+
+    def flops(self):
+        a, b = C.c_double(), C.c_double()
+        self.check(self.lib.mra_last_flops(self.h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
+    def profile_enable(self, on=True):
+        self.check(self.lib.mra_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.lib.mra_profile_read(self.h, buf, C.c_size_t(len(buf))))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n, fl, by = line.split()
+            out[name] = dict(ms=float(ms), launches=int(n), flops=float(fl), bytes=float(by))
+        return out
+
+    def debug_fetch(self, what, node=0, count=None):
+        count = (1 << 24) if count is None else int(count)
+        buf = np.empty(count)
+        n = self.lib.mra_debug_fetch(self.h, what.encode(), int(node), _dptr(buf), C.c_int64(count))
+        if n < 0:
+            self.check(int(n))
+        return buf[:n].copy()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mra_destroy(self.h)
+            self.h = None
+            self.ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -48,12 +48,15 @@ def test_refit_equals_fresh_construction():
     assert np.array_equal(m, m2) and np.array_equal(s, s2)
 
 
-def test_non_spd_is_reported():
+def test_errors_cross_the_abi_as_exceptions():
     import pymra_b200.MRATools as mt
     from pymra_b200 import _ffi
     from pymra_b200.MRATree import MRATree
-    locs = np.repeat(mt.genLocations2d(12), 2, axis=0)     # duplicated locations -> singular knots
-    obs = np.zeros((len(locs), 1))
-    np.random.seed(0)
+    g = load_golden("g48_m32")
+    t = tree_for(g)
     with pytest.raises(_ffi.MraError):
-        MRATree(locs, 200 if False else 16, lambda a, b: mt.ExpCovFun(a, b, l=0.5), obs, 1e-2, M=1)
+        t.refit(R=-1.0)                                   # mra_set_nugget rejects it (MRA_ERR_ARG)
+    with pytest.raises(TypeError):
+        MRATree(g["locs"], 8, lambda a, b: mt.ExpCovFun(a, b, l=0.3), g["obs"], np.eye(len(g["locs"])))
+    with pytest.raises(ValueError):
+        MRATree(g["locs"], 8, lambda a, b: mt.ExpCovFun(a, b, l=0.3), g["obs"].ravel(), 1e-2)
