@@ -30,7 +30,8 @@ enum mra_status {
   MRA_ERR_CUDA = -2,       /* CUDA runtime error */
   MRA_ERR_STATE = -3,      /* call order violated */
   MRA_ERR_NOT_SPD = -4,    /* a Cholesky factorisation met a non-positive pivot */
-  MRA_ERR_NOMEM = -5       /* workspace too small */
+  MRA_ERR_NOMEM = -5,      /* workspace / output arrays too small */
+  MRA_BUILD_UNSUPPORTED = 1 /* mra_build_structure_2d met a node outside its fast path (not an error) */
 };
 
 enum mra_cov_family {      /* pyMRA/MRATools.py */
@@ -69,6 +70,20 @@ int mra_create(mra_handle **out, int device);
 int mra_destroy(mra_handle *h);
 const char *mra_last_error(const mra_handle *h);
 const char *mra_version(void);
+
+/* Native host builder of the tree for 2-D inputs whose internal nodes all have > 100 rows and
+ * > 100 knot candidates (random knots + quadrant splits, MRANode.py:36-38, 56-57, 191-193, 232-239).
+ * Consumes/advances the legacy NumPy MT19937 state (key[624], pos) exactly like the reference's
+ * np.random.choice calls in DFS pre-order, including the fork semantics at critDepth.  All output
+ * arrays are caller-allocated (max_nodes entries; knot_rows/kinds_local max_nodes*r; perm n_locs).
+ * Returns MRA_BUILD_UNSUPPORTED (RNG state untouched) if a node needs the KMeans/1-D paths. */
+int mra_build_structure_2d(const double *locs, int64_t n_locs, int32_t r, int32_t M, int32_t J,
+                           int32_t critDepth, uint32_t *mt_key, int32_t *mt_pos, int32_t max_nodes,
+                           int32_t *n_nodes_out, int32_t *depth_out, int32_t *node_level,
+                           int32_t *node_parent, int32_t *node_kind, int64_t *node_row_start,
+                           int64_t *node_row_count, int32_t *node_child_start, int32_t *node_child_count,
+                           int64_t *node_knot_off, int64_t *knot_rows, int32_t *kinds_local,
+                           int64_t *n_knot_rows_out, int64_t *perm, int32_t *dfs_index);
 
 /* Tree/knot/partition indexing computed on the host (bit-exact to MRANode.py:23-98,
  * 179-242, 289-340); copied into the handle. */

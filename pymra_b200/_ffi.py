@@ -33,6 +33,9 @@ SIGNATURES = {
     "mra_destroy": (C.c_int, [C.c_void_p]),
     "mra_last_error": (C.c_char_p, [C.c_void_p]),
     "mra_version": (C.c_char_p, []),
+    "mra_build_structure_2d": (C.c_int, [_pd, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.POINTER(C.c_uint32), _p32, C.c_int32, _p32, _p32, _p32, _p32, _p32,
+                                         _p64, _p64, _p32, _p32, _p64, _p64, _p32, _p64, _p64, _p32]),
     "mra_set_structure": (C.c_int, [C.c_void_p, C.POINTER(MraStructure)]),
     "mra_plan": (C.c_int, [C.c_void_p, _pd, C.c_int, C.POINTER(C.c_size_t)]),
     "mra_bind_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -107,12 +107,118 @@ def _partition_small(X, d, J, kinds, rest):
     return parts
 
 
-def build_structure(locs, r, M, J, critDepth):
+def _ids_from_parents(parent, child_start, child_count):
+    ids = [""] * len(parent)
+    ids[0] = "r"
+    for n in range(len(parent)):
+        for j in range(int(child_count[n])):
+            ids[int(child_start[n]) + j] = ids[n] + str(j + 1)
+    return ids
+
+
+def build_structure_native(locs, r, M, J, critDepth):
+    """The C++ builder (csrc/mra_structure.cpp) for the large-node 2-D path; returns None (global
+    RNG untouched) when the tree needs the KMeans / 1-D paths."""
+    import ctypes as C
+
+    from . import _ffi
+    locs = np.ascontiguousarray(locs, dtype=np.float64)
+    N, d = locs.shape
+    if d != 2 or N >= 2 ** 31 or N <= 100:
+        return None
+    state = np.random.get_state()
+    if state[0] != "MT19937":
+        return None
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = C.c_int32(int(state[2]))
+    max_nodes = sum(4 ** m for m in range(M + 1))
+    if max_nodes > 50_000_000:
+        return None
+    i32 = lambda n: np.zeros(max(1, n), dtype=np.int32)
+    i64 = lambda n: np.zeros(max(1, n), dtype=np.int64)
+    lvl, par, kind, cst, ccnt, dfs = (i32(max_nodes) for _ in range(6))
+    rs, rc, koff = (i64(max_nodes) for _ in range(3))
+    knots = i64(max_nodes * r)
+    kloc = i32(max_nodes * r)
+    perm = i64(N)
+    nn, depth, nk = C.c_int32(), C.c_int32(), C.c_int64()
+    p32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    rcode = _ffi.lib().mra_build_structure_2d(
+        locs.ctypes.data_as(C.POINTER(C.c_double)), N, r, M, J, critDepth,
+        key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(pos), max_nodes, C.byref(nn), C.byref(depth),
+        p32(lvl), p32(par), p32(kind), p64(rs), p64(rc), p32(cst), p32(ccnt), p64(koff), p64(knots), p32(kloc),
+        C.byref(nk), p64(perm), p32(dfs))
+    if rcode == 1:
+        return None
+    if rcode != 0:
+        raise StructureError("native structure builder failed with status %d" % rcode)
+    np.random.set_state((state[0], key, int(pos.value), state[3], state[4]))
+    n = int(nn.value)
+    st = TreeStructure()
+    st.N, st.d, st.r, st.J, st.M = N, d, r, J, M
+    st.depth = int(depth.value)
+    st.perm = perm
+    st.node_level, st.node_parent, st.node_kind = lvl[:n].copy(), par[:n].copy(), kind[:n].copy()
+    st.node_row_start, st.node_row_count = rs[:n].copy(), rc[:n].copy()
+    st.node_child_start, st.node_child_count = cst[:n].copy(), ccnt[:n].copy()
+    st.node_knot_off = koff[:n].copy()
+    st.knot_rows = knots[: int(nk.value)].copy()
+    st.level_off = np.searchsorted(st.node_level, np.arange(st.depth + 2)).astype(np.int32)
+    st.node_id = _LazyIds(st)
+    st.node_kinds_local = _LazyKinds(st, kloc[: int(nk.value)].copy())
+    return st
+
+
+class _LazyIds(object):
+    def __init__(self, st):
+        self._st, self._ids = st, None
+
+    def _get(self):
+        if self._ids is None:
+            self._ids = _ids_from_parents(self._st.node_parent, self._st.node_child_start, self._st.node_child_count)
+        return self._ids
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __len__(self):
+        return self._st.n_nodes
+
+
+class _LazyKinds(object):
+    """node_kinds_local for natively built trees: internal nodes from the builder's output, leaves
+    (all rows that are no ancestor's knot) reconstructed on demand."""
+
+    def __init__(self, st, kloc):
+        self._st, self._kloc = st, kloc
+
+    def __getitem__(self, n):
+        st = self._st
+        if st.node_kind[n] == KIND_INTERNAL:
+            o = int(st.node_knot_off[n])
+            return self._kloc[o:o + st.r].astype(np.int64)
+        s, c = int(st.node_row_start[n]), int(st.node_row_count[n])
+        isk = np.zeros(st.N, dtype=bool)
+        isk[st.knot_rows] = True
+        return np.flatnonzero(~isk[s:s + c]).astype(np.int64)
+
+    def __len__(self):
+        return self._st.n_nodes
+
+
+def build_structure(locs, r, M, J, critDepth, native=True):
     """Build the tree for already-resolved (M, J, critDepth) (see MRATree.__init__).
 
-    Consumes the global NumPy RNG exactly like the reference constructor would.
+    Consumes the global NumPy RNG exactly like the reference constructor would.  The native
+    builder is used when the whole tree stays on the large-node 2-D path; otherwise (or with
+    native=False) the NumPy builder below runs.
     """
     locs = np.ascontiguousarray(locs, dtype=np.float64)
+    if native and locs.ndim == 2 and locs.shape[1] == 2:
+        st = build_structure_native(locs, r, M, J, critDepth)
+        if st is not None:
+            return st
     if locs.ndim != 2:
         raise StructureError("locs must be (N, d)")
     N, d = locs.shape
