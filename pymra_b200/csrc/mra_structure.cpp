@@ -111,11 +111,29 @@ struct Builder {
     // ---- knots: permutation(n_nk)[:r] mapped through the not-knot list, sorted
     int32_t* a = scratch.data();
     for (int64_t i = 0; i < n_nk; ++i) a[i] = (int32_t)i;
-    for (int64_t i = n_nk - 1; i >= 1; --i) {
-      uint32_t j = rng.interval((uint32_t)i);
-      int32_t t = a[i];
-      a[i] = a[j];
-      a[j] = t;
+    {
+      // Fisher-Yates from the top; the draws do not depend on the array, so they are generated
+      // LA steps ahead (same order, same stream) and their targets prefetched.
+      constexpr int LA = 64;
+      uint32_t jq[LA];
+      int64_t gen_i = n_nk - 1;
+      for (int s0 = 0; s0 < LA && gen_i >= 1; ++s0, --gen_i) {
+        jq[s0] = rng.interval((uint32_t)gen_i);
+        __builtin_prefetch(&a[jq[s0]], 1);
+      }
+      int slot = 0;
+      for (int64_t i = n_nk - 1; i >= 1; --i) {
+        const uint32_t j = jq[slot];
+        if (gen_i >= 1) {
+          jq[slot] = rng.interval((uint32_t)gen_i);
+          __builtin_prefetch(&a[jq[slot]], 1);
+          --gen_i;
+        }
+        slot = (slot + 1 == LA) ? 0 : slot + 1;
+        const int32_t t = a[i];
+        a[i] = a[j];
+        a[j] = t;
+      }
     }
     std::vector<int32_t> pick(a, a + r);
     std::sort(pick.begin(), pick.end());

@@ -52,7 +52,7 @@ def test_cov_introspection(d):
 
 def test_capi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "pymra_b200.h")).read()
-    declared = set(re.findall(r"\b(mra_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(mra_[a-z_0-9]+)\s*\(", hdr))
     assert declared and declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
     assert os.path.exists(_ffi.LIB_PATH), "run __graft_entry__.build() first"
     lib = ctypes.CDLL(_ffi.LIB_PATH)
