@@ -128,27 +128,55 @@ DevCtx make_ctx(mra_handle* h) {
   return c;
 }
 
-size_t smem_knot(int r) { return sizeof(double) * ((size_t)r * (r + 1) + 3 * r + 2 * TB * LDT) + sizeof(int) * r + 16; }
+constexpr size_t GS = sizeof(GemmSmem);
+size_t smem_knot(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + 3 * r) + sizeof(int) * r + 16; }
 size_t smem_prior(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;
-  return sizeof(double) * ((size_t)TB * ldT + 2 * TB * LDT + 2 * r + 2 * TB);
+  return GS + sizeof(double) * ((size_t)TB * ldT + 2 * r + 2 * TB);
 }
-size_t smem_chol() { return sizeof(double) * ((size_t)2 * TB * LDB + TB + 2 * TB * LDT); }
-size_t smem_solve() { return sizeof(double) * ((size_t)TB * LDB + 2 * TB * LDT); }
-size_t smem_factor(int r) { return sizeof(double) * ((size_t)r * (r + 1) + r + 2 * TB * LDT); }
+size_t smem_gram() { return GS + sizeof(int) * 2 * TB; }
+size_t smem_chol() { return GS + sizeof(double) * ((size_t)2 * TB * LDB + TB); }
+size_t smem_solve() { return GS + sizeof(double) * ((size_t)TB * LDB); }
+size_t smem_plain() { return GS; }
+size_t smem_factor(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + r); }
 size_t smem_predict(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;
-  return sizeof(double) * ((size_t)TB * ldT + 2 * TB * LDT);
+  return GS + sizeof(double) * ((size_t)TB * ldT);
+}
+
+// Kernels are instantiated for VEC = 2 (16-byte cp.async, even r) and VEC = 1 (odd r).
+#define MRA_FOR_VEC(h, expr)         \
+  do {                               \
+    if (((h)->r & 1) == 0) {         \
+      constexpr int V_ = 2;          \
+      expr;                          \
+    } else {                         \
+      constexpr int V_ = 1;          \
+      expr;                          \
+    }                                \
+  } while (0)
+
+template <int V_>
+cudaError_t configure_vec(int r) {
+  cudaError_t e;
+#define SET_(k, bytes)                                                                         \
+  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));      \
+  if (e != cudaSuccess) return e
+  SET_(k_knot_factor<V_>, smem_knot(r));
+  SET_(k_prior_tiles<V_>, smem_prior(r));
+  SET_(k_leaf_gram<V_>, smem_gram());
+  SET_(k_leaf_chol_step<V_>, smem_chol());
+  SET_(k_leaf_solve<V_>, smem_solve());
+  SET_(k_assemble_A<V_>, smem_plain());
+  SET_(k_node_factor<V_>, smem_factor(r));
+  SET_(k_leaf_apply<V_>, smem_plain());
+  SET_(k_predict_level<V_>, smem_predict(r));
+#undef SET_
+  return cudaSuccess;
 }
 
 int configure_kernels(mra_handle* h) {
-  const int r = h->r;
-  CU(cudaFuncSetAttribute(k_knot_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_knot(r)));
-  CU(cudaFuncSetAttribute(k_prior_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prior(r)));
-  CU(cudaFuncSetAttribute(k_leaf_chol_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol()));
-  CU(cudaFuncSetAttribute(k_leaf_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve()));
-  CU(cudaFuncSetAttribute(k_node_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_factor(r)));
-  CU(cudaFuncSetAttribute(k_predict_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_predict(r)));
+  MRA_FOR_VEC(h, CU(configure_vec<V_>(h->r)));
   return MRA_OK;
 }
 
@@ -228,10 +256,10 @@ int launch_likelihood(mra_handle* h, cudaStream_t st) {
     const int nn = (int)h->internal_at[m].size();
     if (!nn) continue;
     const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
-    LAUNCH("knot_factor", k_knot_factor<<<nn, NT, smem_knot(r), st>>>(c, list));
+    MRA_FOR_VEC(h, LAUNCH("knot_factor", k_knot_factor<V_><<<nn, NT, smem_knot(r), st>>>(c, list)));
     const int ntile = (int)h->tiles_at[m].size();
     const int4* tiles = reinterpret_cast<const int4*>(h->ws + L.tiles + h->tiles_off[m]);
-    LAUNCH("prior_tiles", k_prior_tiles<<<ntile, NT, smem_prior(r), st>>>(c, tiles, m));
+    MRA_FOR_VEC(h, LAUNCH("prior_tiles", k_prior_tiles<V_><<<ntile, NT, smem_prior(r), st>>>(c, tiles, m)));
   }
   // ---- leaves
   const int nleaf = (int)h->leaves.size();
@@ -239,13 +267,13 @@ int launch_likelihood(mra_handle* h, cudaStream_t st) {
   if (nleaf && h->max_leaf_obs > 0) {
     const int nbo = (h->max_leaf_obs + TB - 1) / TB;
     dim3 g1(nleaf, nbo * (nbo + 1) / 2);
-    LAUNCH("leaf_gram", k_leaf_gram<<<g1, NT, 0, st>>>(c, leaf_list, 0));
+    MRA_FOR_VEC(h, LAUNCH("leaf_gram", k_leaf_gram<V_><<<g1, NT, smem_gram(), st>>>(c, leaf_list, 0)));
     for (int p = 0; p < nbo; ++p) {
       dim3 g2(nleaf, nbo - p);
-      LAUNCH("leaf_chol", k_leaf_chol_step<<<g2, NT, smem_chol(), st>>>(c, leaf_list, p));
+      MRA_FOR_VEC(h, LAUNCH("leaf_chol", k_leaf_chol_step<V_><<<g2, NT, smem_chol(), st>>>(c, leaf_list, p)));
     }
     dim3 g3(nleaf, (h->max_leaf_W + TB - 1) / TB);
-    LAUNCH("leaf_solve", k_leaf_solve<<<g3, NT, smem_solve(), st>>>(c, leaf_list, 0));
+    MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve<V_><<<g3, NT, smem_solve(), st>>>(c, leaf_list, 0)));
   }
   // ---- upward
   for (int m = (int)h->internal_at.size() - 1; m >= 0; --m) {
@@ -254,9 +282,8 @@ int launch_likelihood(mra_handle* h, cudaStream_t st) {
     const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
     const int W = (m + 1) * r + 1, nb = (W + TB - 1) / TB;
     dim3 ga(nn, nb * (nb + 1) / 2);
-    LAUNCH("assemble_A", k_assemble_A<<<ga, NT, 0, st>>>(c, list));
-    dim3 gf(nn, (m * r + 1 + TB - 1) / TB);
-    LAUNCH("node_factor", k_node_factor<<<gf, NT, smem_factor(r), st>>>(c, list));
+    MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<ga, NT, smem_plain(), st>>>(c, list)));
+    MRA_FOR_VEC(h, LAUNCH("node_factor", k_node_factor<V_><<<nn, NT, smem_factor(r), st>>>(c, list)));
   }
   LAUNCH("finalize", k_finalize<<<1, NT, 0, st>>>(c, at<double>(h, L.out)));
   CU(cudaGetLastError());
@@ -276,17 +303,17 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
     if (h->max_leaf_obs > 0) {
       const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
       dim3 g1(nleaf, nbr * nbo);
-      LAUNCH("leaf_gram_T", k_leaf_gram<<<g1, NT, 0, st>>>(c, leaf_list, 1));
+      MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<g1, NT, smem_gram(), st>>>(c, leaf_list, 1)));
       dim3 g2(nleaf, nbr);
-      LAUNCH("leaf_solve_Q", k_leaf_solve<<<g2, NT, smem_solve(), st>>>(c, leaf_list, 1));
+      MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", k_leaf_solve<V_><<<g2, NT, smem_solve(), st>>>(c, leaf_list, 1)));
       dim3 g3(nleaf, nbr * ((h->max_leaf_W + TB - 1) / TB));
-      LAUNCH("leaf_apply", k_leaf_apply<<<g3, NT, 0, st>>>(c, leaf_list));
+      MRA_FOR_VEC(h, LAUNCH("leaf_apply", k_leaf_apply<V_><<<g3, NT, smem_plain(), st>>>(c, leaf_list)));
     }
     for (int m = (int)h->internal_at.size() - 1; m >= 0; --m) {
       const int ntile = (int)h->tiles_at[m].size();
       if (!ntile) continue;
       const int4* tiles = reinterpret_cast<const int4*>(h->ws + L.tiles + h->tiles_off[m]);
-      LAUNCH("predict_level", k_predict_level<<<ntile, NT, smem_predict(r), st>>>(c, tiles, m));
+      MRA_FOR_VEC(h, LAUNCH("predict_level", k_predict_level<V_><<<ntile, NT, smem_predict(r), st>>>(c, tiles, m)));
     }
     h->pred_done = true;   // V now holds the posterior-updated basis; results stay cached in mean/var
   }

@@ -1,0 +1,201 @@
+// FP64 tile GEMM core of the MRA kernels (sm_100a).
+//
+// One primitive: a 64x64 accumulator tile per 128-thread CTA (4 warps, 2x2 of 32x32),
+//     acc += A(64 x K) * B(64 x K)^T,   both operands K-contiguous ("NT"),
+// computed with FP64 tensor-core MMA (mma.sync m8n8k4 -> SASS DMMA.8x8x4, the only FP64 MMA
+// shape sm_100a has).  Operands living in global memory are streamed through a 3-stage
+// cp.async (LDGSTS) pipeline of 64 x 16 chunks; the chunks are stored with an XOR swizzle of
+// their 16-byte columns so the 8x4 fragment loads are bank-conflict free without padding.
+// Operands that already live in shared memory (the T / D / P tiles of the callers) are read in
+// place through an element functor.
+//
+// Row sources are described by a functor rr -> const double* (start of the K range of tile row
+// rr, or nullptr for a zero row).  VEC = 2 uses 16-byte copies and needs every row start 16-byte
+// aligned (true whenever r is even: all leading dimensions are even by construction); VEC = 1
+// uses 8-byte copies and has no alignment requirement (odd r).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mra {
+
+constexpr int TB = 64;        // tile rows / cols
+constexpr int KC = 16;        // k chunk per pipeline stage
+constexpr int NT = 128;       // threads per CTA
+constexpr int NSTAGE = 3;     // cp.async pipeline depth
+constexpr int LDB = TB + 4;   // smem row stride of a resident 64x64 block (== 4 mod 16 doubles)
+
+struct GemmSmem {
+  double a[NSTAGE][TB * KC];
+  double b[NSTAGE][TB * KC];
+  const double* row_a[TB];
+  const double* row_b[TB];
+};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+struct Acc {
+  double v[4][4][2];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j][0] = v[i][j][1] = 0.0;
+  }
+  __device__ __forceinline__ void negate() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[i][j][0] = -v[i][j][0];
+        v[i][j][1] = -v[i][j][1];
+      }
+  }
+};
+
+__device__ __forceinline__ void cp_async_16(double* smem, const double* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(double* smem, const double* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// Swizzled position of element (row, k) of a staged 64 x 16 chunk.
+__device__ __forceinline__ int stage_pos(int row, int k) {
+  return row * KC + ((((k >> 1) ^ ((row & 3) << 1)) << 1) | (k & 1));
+}
+
+// Issue the copies of one chunk (k0 .. k0+KC) of one operand.  `dummy` is any valid global address
+// (used with src-size 0, which reads nothing and zero-fills).
+template <int VEC>
+__device__ __forceinline__ void stage_load(double* st, const double* const* rows, int k0, int K,
+                                           const double* dummy) {
+  if (VEC == 2) {
+    const int kc = (threadIdx.x & 7) * 2, rb = threadIdx.x >> 3;
+    const int k = k0 + kc;
+    const int nv = min(max(K - k, 0), 2) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = rb + 16 * i;
+      const double* p = rows[row];
+      cp_async_16(st + stage_pos(row, kc), p ? p + k : dummy, p ? nv : 0);
+    }
+  } else {
+    const int kc = threadIdx.x & 15, rb = threadIdx.x >> 4;
+    const int k = k0 + kc;
+    const int nv = (k < K) ? 8 : 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = rb + 8 * i;
+      const double* p = rows[row];
+      cp_async_8(st + stage_pos(row, kc), p ? p + k : dummy, p ? nv : 0);
+    }
+  }
+}
+
+// 64 x 64 x 16 of DMMA on one chunk.  ga(row, kk) / gb(row, kk): operand element at tile row `row`,
+// k index kk (0..15) inside the chunk.
+template <class GA, class GB>
+__device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < KC; ks += 4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[i] = ga(wm + i * 8 + g, ks + q);
+      b[i] = gb(wn + i * 8 + g, ks + q);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc.v[i][j], a[i], b[j]);
+  }
+}
+
+// acc += A B^T.
+//   A_GLOBAL: fa(rr) -> const double* row pointer (nullptr = zero row); else fa(rr, k) -> element
+//   (shared-memory resident operand; must return 0 for k >= K).  Same for B.
+// Must be called by all 128 threads; safe to call back to back (leading barrier).
+template <int VEC, bool A_GLOBAL, bool B_GLOBAL, class FA, class FB>
+__device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSmem& sm, const double* dummy) {
+  __syncthreads();   // previous users of the stages / row tables (and of resident operands) are done
+  if (A_GLOBAL) {
+    if (threadIdx.x < TB) {
+      if constexpr (A_GLOBAL) sm.row_a[threadIdx.x] = fa((int)threadIdx.x);
+    }
+  }
+  if (B_GLOBAL) {
+    if (threadIdx.x >= NT - TB) {
+      if constexpr (B_GLOBAL) sm.row_b[threadIdx.x - (NT - TB)] = fb((int)threadIdx.x - (NT - TB));
+    }
+  }
+  __syncthreads();
+  const int nk = (K + KC - 1) / KC;
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) {
+    if (s < nk) {
+      if (A_GLOBAL) stage_load<VEC>(sm.a[s], sm.row_a, s * KC, K, dummy);
+      if (B_GLOBAL) stage_load<VEC>(sm.b[s], sm.row_b, s * KC, K, dummy);
+    }
+    cp_async_commit();
+  }
+  int buf = 0;
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();
+    {
+      const int kn = kt + NSTAGE - 1;
+      int nb = buf + NSTAGE - 1;
+      if (nb >= NSTAGE) nb -= NSTAGE;
+      if (kn < nk) {
+        if (A_GLOBAL) stage_load<VEC>(sm.a[nb], sm.row_a, kn * KC, K, dummy);
+        if (B_GLOBAL) stage_load<VEC>(sm.b[nb], sm.row_b, kn * KC, K, dummy);
+      }
+      cp_async_commit();
+    }
+    const double* sa = sm.a[buf];
+    const double* sb = sm.b[buf];
+    const int k0 = kt * KC;
+    auto ga = [&](int row, int kk) -> double {
+      if constexpr (A_GLOBAL) return sa[stage_pos(row, kk)];
+      else return fa(row, k0 + kk);
+    };
+    auto gb = [&](int row, int kk) -> double {
+      if constexpr (B_GLOBAL) return sb[stage_pos(row, kk)];
+      else return fb(row, k0 + kk);
+    };
+    chunk_mma(acc, ga, gb);
+    if (++buf == NSTAGE) buf = 0;
+  }
+  cp_async_wait<0>();
+}
+
+// f(row, col, value) for every accumulator element owned by this thread.
+template <class F>
+__device__ __forceinline__ void tile_epilogue(const Acc& acc, F f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) f(wm + i * 8 + g, wn + j * 8 + q * 2 + e, acc.v[i][j][e]);
+}
+
+}  // namespace mra
