@@ -170,9 +170,25 @@ def run_ours(args, rank, world, local_rank):
     from pymra_b200.session import DeviceSession
     from pymra_b200.structure import build_structure
 
+    import logging
+    logging.getLogger("pymra_b200.MRATree").setLevel(logging.ERROR)   # the M-clamp warning is expected here
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    group = True if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
     n, r, Mreq, family, l, sig, R, frac = WORKLOADS[args.workload]
     N = n * n
     locs, obs = make_inputs(n, frac)
@@ -180,44 +196,41 @@ def run_ours(args, rank, world, local_rank):
     desc = introspect(cov, 2)
     M, J, critDepth, _ = resolve_params(N, 2, r, Mreq, -1, -1)
 
-    if world > 1:
-        raise SystemExit("bench.py: multi-GPU subtree sharding is not wired in yet")
-
     # ---- device-resident timing
     np.random.seed(5)
     t0 = time.time()
     st = build_structure(locs, r, M, J, critDepth)
     t_struct = time.time() - t0
-    sess = DeviceSession(st, locs, obs, want_predict=True)
+    sess = DeviceSession(st, locs, obs, want_predict=True, group=group)
     sess.set_params(desc, R)
     mean_t = torch.empty(N, dtype=torch.float64, device="cuda")
     sd_t = torch.empty(N, dtype=torch.float64, device="cuda")
 
     def step():
         sess.likelihood_async()
-        sess.predict_dev(mean_t, sd_t)
+        sess.predict_dev(mean_t, sd_t, reduce=True)   # N > 1: outputs sum-reduced so every rank holds all N rows
 
     for _ in range(max(args.warmup, 3)):
         step()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     sess.profile_enable(True)
-    torch.cuda.synchronize()
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     lik_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     for i in range(args.steps):
         ev[i][0].record()
         sess.likelihood_async()
         lik_ev[i].record()
-        sess.predict_dev(mean_t, sd_t)
+        sess.predict_dev(mean_t, sd_t, reduce=True)
         ev[i][1].record()
-    torch.cuda.synchronize()
+    barrier()
     launches = sess.launches()
     prof = sess.profile_read()
     sess.profile_enable(False)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     lik_ms = [ev[i][0].elapsed_time(lik_ev[i]) for i in range(args.steps)]
-    total_ms = float(sum(step_ms))
+    total_ms = max_over_ranks(ev[0][0].elapsed_time(ev[-1][1]))   # K steps back to back, slowest rank
     d, u = sess.fetch_likelihood()
     value = args.steps / (total_ms * 1e-3)
     f_lik, f_pred = sess.flops()
@@ -227,17 +240,22 @@ def run_ours(args, rank, world, local_rank):
     t_e2e = []
     lik_e2e = None
     for i in range(1 + e2e_steps):
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.time()
-        tree = MRATree(locs, r, cov, obs, R, M=Mreq)
+        tree = MRATree(locs, r, cov, obs, R, M=Mreq, group=group)
         lik_e2e = float(np.asarray(tree.getLikelihood()).ravel()[0])
         mean_h, sd_h = tree.predict()
-        torch.cuda.synchronize()
+        barrier()
         if i > 0:
-            t_e2e.append(time.time() - t0)
+            t_e2e.append(max_over_ranks(time.time() - t0))
         del tree
     e2e_value = 1.0 / float(np.mean(t_e2e))
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     h2d = N * 8 * 3 + sess.h2d_structure_bytes
     d2h = N * 16 + 16
 
@@ -261,7 +279,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- CPU baseline (rank 0, bounded sample)
     cb = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         evals, locs_s, per = cpu_baseline(r, Mreq, family, l, sig, R, frac, N)
         cb = {"value": evals, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
               "sample": "oracle/mra_oracle.py on a %dx%d grid, r0=%d (one level-3 subtree of the workload, same leaf "
@@ -273,7 +291,10 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "grid": [n, n], "n_locs": N, "r0": r, "M_requested": Mreq,
                        "M_effective": M, "J": J, "cov": family, "l": l, "sig": sig, "R": R, "frac_obs": frac,
-                       "nodes": int(st.n_nodes), "l2_policy": "inputs larger than L2 (basis stack %.1f GB)" % (
+                       "nodes": int(st.n_nodes), "parallelism": ("subtree sharding at level %d over %d GPUs, one "
+                       "all-reduce of %d summary doubles per evaluation + sum-reduce of the outputs" % (
+                           sess.shard_level, world, 0 if sess.summary is None else sess.summary.numel()))
+                       if world > 1 else "single GPU", "l2_policy": "inputs larger than L2 (basis stack %.1f GB)" % (
                            N * max(st.depth, 1) * r * 8 / 1e9),
                        "step": "likelihood pass + predict pass on a frozen tree, inputs resident in HBM"},
             "predict_locations_per_s": value * N,
@@ -284,11 +305,14 @@ def run_ours(args, rank, world, local_rank):
                     "what": "MRATree(locs, r, cov, obs, R, M) + getLikelihood() + predict(), host numpy in/out, "
                             "fresh knot draw per construction (reference RNG semantics)",
                     "likelihood": lik_e2e},
-            "gpu_launches": int(launches * args.steps),
+            "gpu_launches": int(launches * args.steps * world),
             "roofline": roofline, "kernels": kern, "cpu_baseline": cb, "clocks": clocks,
             "algorithmic_flops": {"likelihood": f_lik, "predict": f_pred},
             "workspace_gb": sess.workspace_bytes / 1e9}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -120,6 +120,25 @@ int mra_run_likelihood_async(mra_handle *h, void *stream);
 int mra_run_predict_dev(mra_handle *h, void *stream, double *dev_mean, double *dev_sd);
 int mra_fetch_likelihood(mra_handle *h, void *stream, double out[2]);
 
+/* Multi-GPU subtree sharding (one process / handle per GPU).  Replaces the reference's fork-per-child
+ * subtree mode (pyMRA/MRANode.py:90-104, 114-115: mp.Process per child at res == critDepth, the child Node
+ * pickled back through a pipe) by one rank per GPU: subtrees rooted at `shard_level` are owned by exactly one
+ * rank, the levels above are replicated.  node_role[n_nodes]: 0 = another rank's subtree, 1 = mine,
+ * 2 = replicated top, 3 = replicated top whose rows this rank emits in predict.  Call after
+ * mra_set_structure and before mra_plan; shard_level == 0 switches sharding off.
+ *
+ * A sharded likelihood evaluation is three steps: mra_run_likelihood_local_async writes the summaries
+ * (A~_c, d_c) of this rank's subtree roots (MRANode.py:474-480, the terms a child hands to its parent) into
+ * the caller's zero-initialised device buffer of mra_summary_size doubles; the caller sum-reduces that buffer
+ * over the ranks (NCCL all-reduce; slots are disjoint, so the sum is exact); mra_run_likelihood_top_async
+ * finishes the replicated levels (MRANode.py:432-468).  mra_run_predict* then produces this rank's rows and
+ * leaves the others zero, so outputs can be sum-reduced as well.  With shard_level == 0 the two calls run
+ * back to back without a buffer (dev_summary may be NULL). */
+int mra_set_shard(mra_handle *h, int32_t shard_level, const int8_t *node_role);
+int mra_summary_size(const mra_handle *h, int64_t *n_doubles);
+int mra_run_likelihood_local_async(mra_handle *h, void *stream, double *dev_summary);
+int mra_run_likelihood_top_async(mra_handle *h, void *stream, const double *dev_summary);
+
 /* Counters for bench.py: kernels launched by the last run_* call, and algorithmic FP64
  * flop of the last likelihood / predict pass as executed. */
 int mra_last_launches(const mra_handle *h, int64_t *n);

@@ -7,6 +7,11 @@ Same constructor signature and semantics as the reference class; the work the re
   * the device library behind the C ABI (include/pymra_b200.h): prior pass, leaf terms, upward
     pass for the likelihood, downward pass for predictions.
 PyTorch only supplies the device arena and the stream.  There is no CPU fallback.
+
+Beyond the reference signature: `device` (CUDA ordinal) and `group` (a torch.distributed process group,
+or True for the default one): every rank of the group constructs the same tree from the same inputs and
+RNG state, whole subtrees are sharded over the ranks' GPUs (pymra_b200/shard.py), and every rank returns
+the full likelihood and predictions.
 """
 import logging
 
@@ -67,7 +72,7 @@ class _Root(object):
 
 class MRATree(object):
 
-    def __init__(self, locs, r, cov, obs, R, M=-1, J=-1, critDepth=-1, verbose=True, device=None):
+    def __init__(self, locs, r, cov, obs, R, M=-1, J=-1, critDepth=-1, verbose=True, device=None, group=None):
         self.locs = locs
         self.d = np.shape(self.locs)[1]
         N = len(locs)
@@ -92,7 +97,7 @@ class MRATree(object):
 
         locs_c = np.ascontiguousarray(locs, dtype=np.float64).reshape(N, self.d)
         self._structure = build_structure(locs_c, r, M, J, critDepth)
-        self._session = DeviceSession(self._structure, locs_c, obs_arr, want_predict=True, device=device)
+        self._session = DeviceSession(self._structure, locs_c, obs_arr, want_predict=True, device=device, group=group)
         self._mom = None
         self._evaluate()
         self.root = _Root(self)

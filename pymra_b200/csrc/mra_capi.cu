@@ -29,7 +29,7 @@ struct Arena {
 
 struct Layout {
   size_t nodes, knot_rows, obs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
-      mean, var, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles;
+      mean, var, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks;
   size_t total;
 };
 
@@ -49,7 +49,17 @@ struct mra_handle {
   // derived lists
   std::vector<std::vector<int>> internal_at;   // node ids per level
   std::vector<int> leaves;                     // node ids of leaves + orphans
-  std::vector<std::vector<int4>> tiles_at;     // 64-row tiles of internal nodes per level
+  std::vector<std::vector<int4>> tiles_at;     // 64-row tiles of internal nodes per level (predict pass)
+  std::vector<std::vector<int4>> ptiles_at;    // prior pass: the same plus gathered knot tiles (sharded runs)
+  std::vector<int> gather_rows;                // row ids of the gathered tiles
+  std::vector<int2> emit_chunks;               // row ranges whose results this rank emits
+  // subtree sharding (mra_set_shard): role per node, 0 = another rank's, 1 = mine, 2 = replicated top,
+  // 3 = replicated top whose rows this rank emits
+  int shard_level = 0;
+  std::vector<int8_t> role;
+  std::vector<int> sroots;                     // my subtree roots at the shard level
+  int slot_base = 0, n_slots = 0;
+  size_t sroots_off = 0;
   std::vector<NodeDev> nodes;
   std::vector<int> obs_rows;
   int max_leaf_obs = 0, max_leaf_rows = 0, max_leaf_W = 1;
@@ -59,7 +69,7 @@ struct mra_handle {
   Layout lay{};
   char* ws = nullptr;
   size_t ws_bytes = 0;
-  std::vector<size_t> list_off, tiles_off;   // per level offsets (bytes) inside lay.lists / lay.tiles
+  std::vector<size_t> list_off, tiles_off, ptiles_off;   // per level offsets (bytes) inside lay.lists / lay.tiles / lay.ptiles
   size_t leaves_off = 0;
   CovParams cov{0, 1.0, 1.0, 1.0};
   double R = 1.0;
@@ -103,6 +113,7 @@ DevCtx make_ctx(mra_handle* h) {
   c.nodes = at<NodeDev>(h, L.nodes);
   c.knot_rows = at<int>(h, L.knot_rows);
   c.obs_rows = at<int>(h, L.obs_rows);
+  c.gather_rows = at<int>(h, L.gather);
   c.xs = at<double>(h, L.xs);
   c.ys = at<double>(h, L.ys);
   c.yobs = at<double>(h, L.yobs);
@@ -132,7 +143,7 @@ constexpr size_t GS = sizeof(GemmSmem);
 size_t smem_knot(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + 3 * r) + sizeof(int) * r + 16; }
 size_t smem_prior(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;
-  return GS + sizeof(double) * ((size_t)TB * ldT + 2 * r + 2 * TB);
+  return GS + sizeof(double) * ((size_t)TB * ldT + 2 * r + 2 * TB) + sizeof(int) * TB;
 }
 size_t smem_gram() { return GS + sizeof(int) * 2 * TB; }
 size_t smem_chol() { return GS + sizeof(double) * ((size_t)2 * TB * LDB + TB); }
@@ -244,7 +255,22 @@ int check_status(mra_handle* h, cudaStream_t st) {
   return MRA_OK;
 }
 
-int launch_likelihood(mra_handle* h, cudaStream_t st) {
+int upward_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m) {
+  const Layout& L = h->lay;
+  const int r = h->r;
+  const int nn = (int)h->internal_at[m].size();
+  if (!nn) return MRA_OK;
+  const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
+  const int W = (m + 1) * r + 1, nb = (W + TB - 1) / TB;
+  dim3 ga(nn, nb * (nb + 1) / 2);
+  MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<ga, NT, smem_plain(), st>>>(c, list, nullptr, 0)));
+  MRA_FOR_VEC(h, LAUNCH("node_factor", k_node_factor<V_><<<nn, NT, smem_factor(r), st>>>(c, list)));
+  return MRA_OK;
+}
+
+// Prior pass, leaf terms and the upward pass down to the shard level (level 0 when not sharded).
+// Sharded: ends by exporting the summaries of this rank's subtree roots into dev_summary.
+int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary) {
   const Layout& L = h->lay;
   DevCtx c = make_ctx(h);
   const int r = h->r;
@@ -257,8 +283,9 @@ int launch_likelihood(mra_handle* h, cudaStream_t st) {
     if (!nn) continue;
     const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
     MRA_FOR_VEC(h, LAUNCH("knot_factor", k_knot_factor<V_><<<nn, NT, smem_knot(r), st>>>(c, list)));
-    const int ntile = (int)h->tiles_at[m].size();
-    const int4* tiles = reinterpret_cast<const int4*>(h->ws + L.tiles + h->tiles_off[m]);
+    const int ntile = (int)h->ptiles_at[m].size();
+    if (!ntile) continue;
+    const int4* tiles = reinterpret_cast<const int4*>(h->ws + L.ptiles + h->ptiles_off[m]);
     MRA_FOR_VEC(h, LAUNCH("prior_tiles", k_prior_tiles<V_><<<ntile, NT, smem_prior(r), st>>>(c, tiles, m)));
   }
   // ---- leaves
@@ -275,15 +302,41 @@ int launch_likelihood(mra_handle* h, cudaStream_t st) {
     dim3 g3(nleaf, (h->max_leaf_W + TB - 1) / TB);
     MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve<V_><<<g3, NT, smem_solve(), st>>>(c, leaf_list, 0)));
   }
-  // ---- upward
-  for (int m = (int)h->internal_at.size() - 1; m >= 0; --m) {
-    const int nn = (int)h->internal_at[m].size();
-    if (!nn) continue;
-    const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
-    const int W = (m + 1) * r + 1, nb = (W + TB - 1) / TB;
-    dim3 ga(nn, nb * (nb + 1) / 2);
-    MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<ga, NT, smem_plain(), st>>>(c, list)));
-    MRA_FOR_VEC(h, LAUNCH("node_factor", k_node_factor<V_><<<nn, NT, smem_factor(r), st>>>(c, list)));
+  // ---- upward, levels >= shard level
+  for (int m = (int)h->internal_at.size() - 1; m >= h->shard_level; --m) {
+    int rc = upward_level(h, st, c, m);
+    if (rc) return rc;
+  }
+  if (h->shard_level > 0 && !h->sroots.empty()) {
+    const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->sroots_off);
+    const int W = h->shard_level * r + 1, nb = (W + TB - 1) / TB;
+    dim3 ga((unsigned)h->sroots.size(), nb * (nb + 1) / 2);
+    MRA_FOR_VEC(h, LAUNCH("export_summary",
+                          k_assemble_A<V_><<<ga, NT, smem_plain(), st>>>(c, list, dev_summary, h->slot_base)));
+  }
+  CU(cudaGetLastError());
+  return MRA_OK;
+}
+
+// The replicated top of the upward pass (levels < shard level) and the final reduction.
+int launch_likelihood_top(mra_handle* h, cudaStream_t st, const double* dev_summary) {
+  const Layout& L = h->lay;
+  DevCtx c = make_ctx(h);
+  const int r = h->r;
+  if (h->shard_level > 0) {
+    const int m = h->shard_level - 1;
+    const int nn = m < (int)h->internal_at.size() ? (int)h->internal_at[m].size() : 0;
+    if (nn) {
+      const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
+      const int W = (m + 1) * r + 1;
+      dim3 g(nn, std::min(64, (W * W + 255) / 256));
+      LAUNCH("assemble_summary", k_assemble_from_summary<<<g, 256, 0, st>>>(c, list, dev_summary, h->slot_base));
+      MRA_FOR_VEC(h, LAUNCH("node_factor", k_node_factor<V_><<<nn, NT, smem_factor(r), st>>>(c, list)));
+    }
+    for (int mm = std::min(m - 1, (int)h->internal_at.size() - 1); mm >= 0; --mm) {
+      int rc = upward_level(h, st, c, mm);
+      if (rc) return rc;
+    }
   }
   LAUNCH("finalize", k_finalize<<<1, NT, 0, st>>>(c, at<double>(h, L.out)));
   CU(cudaGetLastError());
@@ -317,12 +370,94 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
     }
     h->pred_done = true;   // V now holds the posterior-updated basis; results stay cached in mean/var
   }
-  const int N = (int)h->N;
-  LAUNCH("unpermute", k_unpermute<<<(N + 255) / 256, 256, 0, st>>>(c.mean, c.var, at<int>(h, L.perm), N,
-                                                                    dev_mean ? dev_mean : at<double>(h, L.out_mean),
-                                                                    dev_sd ? dev_sd : at<double>(h, L.out_sd)));
+  double* om = dev_mean ? dev_mean : at<double>(h, L.out_mean);
+  double* os = dev_sd ? dev_sd : at<double>(h, L.out_sd);
+  if (h->shard_level > 0) {   // rows of other ranks stay zero so the caller can sum-reduce the outputs
+    CU(cudaMemsetAsync(om, 0, sizeof(double) * h->N, st));
+    CU(cudaMemsetAsync(os, 0, sizeof(double) * h->N, st));
+  }
+  if (!h->emit_chunks.empty())
+    LAUNCH("unpermute", k_unpermute<<<(unsigned)h->emit_chunks.size(), 256, 0, st>>>(
+                            c.mean, c.var, at<int>(h, L.perm), at<int2>(h, L.chunks), om, os));
   CU(cudaGetLastError());
   return MRA_OK;
+}
+
+// Work lists of this rank: internal nodes per level, leaves, 64-row tiles for the prior and predict
+// passes, gathered knot tiles and emit ranges.  Not sharded: everything.  Sharded at level s: my subtrees
+// (role 1) in full, the replicated top (role >= 2) restricted to the rows of my subtrees and of top-level
+// leaves, plus the rows of the top nodes' knots that lie in other ranks' subtrees (needed by knot_factor).
+void build_lists(mra_handle* h) {
+  const int nn = h->n_nodes, s = h->shard_level;
+  const size_t nlev = (size_t)h->depth + 1;
+  h->internal_at.assign(nlev, {});
+  h->tiles_at.assign(nlev, {});
+  h->ptiles_at.assign(nlev, {});
+  h->leaves.clear();
+  h->gather_rows.clear();
+  h->emit_chunks.clear();
+  h->sroots.clear();
+  auto add_tiles = [&](int node, int64_t row0, int64_t cnt) {
+    const int lv = h->level[node];
+    for (int64_t r0 = 0; r0 < cnt; r0 += TB) {
+      int4 t = make_int4(node, (int)(row0 + r0), (int)std::min<int64_t>(TB, cnt - r0), 0);
+      h->tiles_at[lv].push_back(t);
+      h->ptiles_at[lv].push_back(t);
+    }
+  };
+  auto add_emit = [&](int64_t row0, int64_t cnt) {
+    for (int64_t r0 = 0; r0 < cnt; r0 += 2048)
+      h->emit_chunks.push_back(make_int2((int)(row0 + r0), (int)std::min<int64_t>(2048, cnt - r0)));
+  };
+  if (s == 0) {
+    for (int n = 0; n < nn; ++n) {
+      if (h->kind[n] == KIND_INTERNAL) {
+        h->internal_at[h->level[n]].push_back(n);
+        add_tiles(n, h->row_start[n], h->row_count[n]);
+      } else {
+        h->leaves.push_back(n);
+      }
+    }
+    add_emit(0, h->N);
+  } else {
+    std::vector<char> covered((size_t)h->N, 0);
+    for (int n = 0; n < nn; ++n) {
+      const int role = h->role[n], lv = h->level[n];
+      if (!role) continue;
+      const bool internal = h->kind[n] == KIND_INTERNAL;
+      if (internal) h->internal_at[lv].push_back(n);
+      else h->leaves.push_back(n);
+      if (lv == s) h->sroots.push_back(n);
+      const bool piece = (lv == s) || (lv < s && !internal);
+      if (piece) {
+        std::fill(covered.begin() + h->row_start[n], covered.begin() + h->row_start[n] + h->row_count[n], 1);
+        for (int a = h->parent[n]; a >= 0; a = h->parent[a]) add_tiles(a, h->row_start[n], h->row_count[n]);
+        if (role == 1 || role == 3) add_emit(h->row_start[n], h->row_count[n]);
+      }
+      if (lv >= s && internal) add_tiles(n, h->row_start[n], h->row_count[n]);
+    }
+    for (int n = 0; n < nn; ++n) {
+      const int lv = h->level[n];
+      if (h->role[n] < 2 || h->kind[n] != KIND_INTERNAL || lv < 1 || lv >= s) continue;
+      const size_t g0 = h->gather_rows.size();
+      for (int i = 0; i < h->r; ++i) {
+        const int row = h->knot_rows[h->knot_off[n] + i];
+        if (!covered[row]) {
+          covered[row] = 1;   // a knot is used by exactly one node; keeps duplicates out all the same
+          h->gather_rows.push_back(row);
+        }
+      }
+      const int cnt = (int)(h->gather_rows.size() - g0);
+      for (int a = h->parent[n]; a >= 0; a = h->parent[a])
+        for (int r0 = 0; r0 < cnt; r0 += TB)
+          h->ptiles_at[h->level[a]].push_back(make_int4(a, 0, std::min(TB, cnt - r0), (int)(g0 + r0) + 1));
+    }
+  }
+  while (!h->internal_at.empty() && h->internal_at.back().empty()) {
+    h->internal_at.pop_back();
+    h->tiles_at.pop_back();
+    h->ptiles_at.pop_back();
+  }
 }
 
 }  // namespace
@@ -387,30 +522,21 @@ int mra_set_structure(mra_handle* h, const mra_structure* s) {
     if (s->perm[i] < 0 || s->perm[i] >= h->N) return fail(h, MRA_ERR_ARG, "perm entry out of range");
     h->perm[i] = (int)s->perm[i];
   }
-  h->internal_at.assign(s->depth + 1, {});
-  h->tiles_at.assign(s->depth + 1, {});
-  h->leaves.clear();
   for (int n = 0; n < nn; ++n) {
     const int lv = h->level[n];
     if (lv < 0 || lv > s->depth) return fail(h, MRA_ERR_ARG, "node level out of range");
     if (h->row_start[n] < 0 || h->row_start[n] + h->row_count[n] > h->N)
       return fail(h, MRA_ERR_ARG, "node row range out of bounds");
+    if (h->parent[n] >= n) return fail(h, MRA_ERR_ARG, "nodes must be numbered level by level (parent before child)");
     if (h->kind[n] == KIND_INTERNAL) {
       if (h->knot_off[n] < 0 || h->knot_off[n] + h->r > s->n_knot_rows)
         return fail(h, MRA_ERR_ARG, "internal node without r knots");
       if (h->child_count[n] <= 0) return fail(h, MRA_ERR_ARG, "internal node without children");
-      h->internal_at[lv].push_back(n);
-      for (int64_t r0 = 0; r0 < h->row_count[n]; r0 += TB)
-        h->tiles_at[lv].push_back(make_int4(n, (int)(h->row_start[n] + r0),
-                                            (int)std::min<int64_t>(TB, h->row_count[n] - r0), 0));
-    } else {
-      h->leaves.push_back(n);
     }
   }
-  while (!h->internal_at.empty() && h->internal_at.back().empty()) {
-    h->internal_at.pop_back();
-    h->tiles_at.pop_back();
-  }
+  h->shard_level = 0;
+  h->role.assign(nn, 1);
+  build_lists(h);
   h->ldv = std::max<long long>(2, ((long long)std::max(h->depth, 1) * h->r + 1) / 2 * 2);
   h->has_structure = true;
   h->planned = h->bound = h->uploaded = h->lik_done = h->pred_done = false;
@@ -441,6 +567,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
     d.row_count = (int)h->row_count[n];
     d.knot_off = (int)h->knot_off[n];
     d.W = d.level * r + 1;
+    if (!h->role[n]) continue;       // another rank's subtree
     const double Kv = (double)d.level * r;
     if (d.kind == KIND_INTERNAL) {
       const int Wa = (d.level + 1) * r + 1;
@@ -541,17 +668,25 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.out_sd = ar.take(D * N);
   h->list_off.assign(h->internal_at.size(), 0);
   h->tiles_off.assign(h->internal_at.size(), 0);
-  size_t lo = 0, to = 0;
+  h->ptiles_off.assign(h->internal_at.size(), 0);
+  size_t lo = 0, to = 0, po = 0;
   for (size_t m = 0; m < h->internal_at.size(); ++m) {
     h->list_off[m] = lo;
     lo += (sizeof(int) * h->internal_at[m].size() + 255) & ~size_t(255);
     h->tiles_off[m] = to;
     to += (sizeof(int4) * h->tiles_at[m].size() + 255) & ~size_t(255);
+    h->ptiles_off[m] = po;
+    po += (sizeof(int4) * h->ptiles_at[m].size() + 255) & ~size_t(255);
   }
   h->leaves_off = lo;
   lo += (sizeof(int) * h->leaves.size() + 255) & ~size_t(255);
+  h->sroots_off = lo;
+  lo += (sizeof(int) * h->sroots.size() + 255) & ~size_t(255);
   L.lists = ar.take(std::max<size_t>(256, lo));
   L.tiles = ar.take(std::max<size_t>(256, to));
+  L.ptiles = ar.take(std::max<size_t>(256, po));
+  L.gather = ar.take(std::max<size_t>(256, sizeof(int) * h->gather_rows.size()));
+  L.chunks = ar.take(std::max<size_t>(256, sizeof(int2) * h->emit_chunks.size()));
   L.total = ar.off;
   *workspace_bytes = L.total;
   h->planned = true;
@@ -594,7 +729,19 @@ int mra_upload_data(mra_handle* h, const double* locs, const double* obs, void* 
     if (!h->tiles_at[m].empty())
       CU(cudaMemcpyAsync(h->ws + L.tiles + h->tiles_off[m], h->tiles_at[m].data(),
                          sizeof(int4) * h->tiles_at[m].size(), cudaMemcpyHostToDevice, st));
+    if (!h->ptiles_at[m].empty())
+      CU(cudaMemcpyAsync(h->ws + L.ptiles + h->ptiles_off[m], h->ptiles_at[m].data(),
+                         sizeof(int4) * h->ptiles_at[m].size(), cudaMemcpyHostToDevice, st));
   }
+  if (!h->sroots.empty())
+    CU(cudaMemcpyAsync(h->ws + L.lists + h->sroots_off, h->sroots.data(), sizeof(int) * h->sroots.size(),
+                       cudaMemcpyHostToDevice, st));
+  if (!h->gather_rows.empty())
+    CU(cudaMemcpyAsync(h->ws + L.gather, h->gather_rows.data(), sizeof(int) * h->gather_rows.size(),
+                       cudaMemcpyHostToDevice, st));
+  if (!h->emit_chunks.empty())
+    CU(cudaMemcpyAsync(h->ws + L.chunks, h->emit_chunks.data(), sizeof(int2) * h->emit_chunks.size(),
+                       cudaMemcpyHostToDevice, st));
   if (!h->leaves.empty())
     CU(cudaMemcpyAsync(h->ws + L.lists + h->leaves_off, h->leaves.data(), sizeof(int) * h->leaves.size(),
                        cudaMemcpyHostToDevice, st));
@@ -632,12 +779,70 @@ int mra_set_nugget(mra_handle* h, double R) {
   return MRA_OK;
 }
 
-int mra_run_likelihood_async(mra_handle* h, void* stream) {
-  if (!h) return MRA_ERR_ARG;
+static int ready_to_run(mra_handle* h) {
   if (!h->uploaded) return fail(h, MRA_ERR_STATE, "mra_upload_data must be called first");
   if (!h->cov_set || !h->R_set) return fail(h, MRA_ERR_STATE, "mra_set_cov and mra_set_nugget must be called first");
   CU(cudaSetDevice(h->device));
-  return launch_likelihood(h, static_cast<cudaStream_t>(stream));
+  return MRA_OK;
+}
+
+int mra_run_likelihood_async(mra_handle* h, void* stream) {
+  if (!h) return MRA_ERR_ARG;
+  if (h->shard_level > 0)
+    return fail(h, MRA_ERR_STATE, "sharded handle: use mra_run_likelihood_local_async / _top_async");
+  int rc = ready_to_run(h);
+  if (rc) return rc;
+  rc = launch_likelihood_local(h, static_cast<cudaStream_t>(stream), nullptr);
+  if (rc) return rc;
+  return launch_likelihood_top(h, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int mra_set_shard(mra_handle* h, int32_t shard_level, const int8_t* node_role) {
+  if (!h) return MRA_ERR_ARG;
+  if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
+  if (shard_level == 0) {
+    h->shard_level = 0;
+    h->role.assign(h->n_nodes, 1);
+  } else {
+    if (!node_role) return MRA_ERR_ARG;
+    if (shard_level < 1 || shard_level > h->depth) return fail(h, MRA_ERR_ARG, "shard level outside the tree");
+    for (int n = 0; n < h->n_nodes; ++n) {
+      const int lv = h->level[n], ro = node_role[n];
+      const bool ok = lv < shard_level ? (ro == 2 || ro == 3)
+                                       : (lv == shard_level ? (ro == 0 || ro == 1) : ro == node_role[h->parent[n]]);
+      if (!ok) return fail(h, MRA_ERR_ARG, "inconsistent node roles");
+    }
+    h->shard_level = shard_level;
+    h->role.assign(node_role, node_role + h->n_nodes);
+  }
+  h->slot_base = shard_level ? h->level_off[shard_level] : 0;
+  h->n_slots = shard_level ? h->level_off[shard_level + 1] - h->level_off[shard_level] : 0;
+  build_lists(h);
+  h->planned = h->bound = h->uploaded = h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+int mra_summary_size(const mra_handle* h, int64_t* n_doubles) {
+  if (!h || !n_doubles) return MRA_ERR_ARG;
+  const int64_t W = (int64_t)h->shard_level * h->r + 1;
+  *n_doubles = h->shard_level ? (int64_t)h->n_slots * (W * W + 1) : 0;
+  return MRA_OK;
+}
+
+int mra_run_likelihood_local_async(mra_handle* h, void* stream, double* dev_summary) {
+  if (!h) return MRA_ERR_ARG;
+  if (h->shard_level > 0 && !dev_summary) return fail(h, MRA_ERR_ARG, "sharded handle needs a summary buffer");
+  int rc = ready_to_run(h);
+  if (rc) return rc;
+  return launch_likelihood_local(h, static_cast<cudaStream_t>(stream), dev_summary);
+}
+
+int mra_run_likelihood_top_async(mra_handle* h, void* stream, const double* dev_summary) {
+  if (!h) return MRA_ERR_ARG;
+  if (h->shard_level > 0 && !dev_summary) return fail(h, MRA_ERR_ARG, "sharded handle needs a summary buffer");
+  int rc = ready_to_run(h);
+  if (rc) return rc;
+  return launch_likelihood_top(h, static_cast<cudaStream_t>(stream), dev_summary);
 }
 
 int mra_fetch_likelihood(mra_handle* h, void* stream, double out[2]) {

@@ -20,7 +20,11 @@ def _dptr(a):
 
 
 class DeviceSession(object):
-    def __init__(self, structure, locs, obs, want_predict=True, device=None):
+    def __init__(self, structure, locs, obs, want_predict=True, device=None, group=None, emulate=None):
+        """group: a torch.distributed process group (or True for the default group) to shard whole
+        subtrees across its ranks, one GPU per rank (pymra_b200/shard.py); None = single GPU.
+        emulate=(world, rank): build the shard of `rank` without a process group; the caller drives
+        likelihood_local_async / likelihood_top_async and reduces `summary` itself (single-GPU tests)."""
         torch = _torch()
         self.structure = structure
         self.N = structure.N
@@ -31,6 +35,23 @@ class DeviceSession(object):
         if st != 0:
             raise _ffi.MraError(st, "mra_create failed (no usable CUDA device?)")
         self._set_structure()
+        self.group, self.world, self.rank, self.shard_level, self.summary = None, 1, 0, 0, None
+        if group is not None or emulate is not None:
+            from .shard import plan_shards
+            if emulate is not None:
+                self.world, self.rank = emulate
+            else:
+                import torch.distributed as dist
+                self.group = None if group is True else group
+                self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            s, role, _ = plan_shards(structure, self.world, self.rank)
+            if s:
+                role = np.ascontiguousarray(role, dtype=np.int8)
+                self.check(self.lib.mra_set_shard(self.h, s, role.ctypes.data_as(C.POINTER(C.c_int8))))
+                n = C.c_int64()
+                self.check(self.lib.mra_summary_size(self.h, C.byref(n)))
+                self.summary = torch.zeros(int(n.value), dtype=torch.float64, device=self.dev)
+                self.shard_level = s
         obs_c = np.ascontiguousarray(np.asarray(obs, dtype=np.float64).reshape(self.N))
         locs_c = np.ascontiguousarray(np.asarray(locs, dtype=np.float64).reshape(self.N, structure.d))
         nbytes = C.c_size_t()
@@ -82,12 +103,26 @@ class DeviceSession(object):
 
     # ---- passes
     def likelihood(self):
-        out = (C.c_double * 2)()
-        self.check(self.lib.mra_run_likelihood(self.h, self.stream(), out))
-        return float(out[0]), float(out[1])
+        self.likelihood_async()
+        return self.fetch_likelihood()
 
     def likelihood_async(self):
-        self.check(self.lib.mra_run_likelihood_async(self.h, self.stream()))
+        if not self.shard_level:
+            self.check(self.lib.mra_run_likelihood_async(self.h, self.stream()))
+            return
+        import torch.distributed as dist
+        self.likelihood_local_async()
+        dist.all_reduce(self.summary, group=self.group)       # disjoint slots: the sum is exact
+        self.likelihood_top_async()
+
+    def likelihood_local_async(self):
+        """Sharded step 1: prior + leaves + upward pass of my subtrees; my summaries land in self.summary."""
+        self.summary.zero_()
+        self.check(self.lib.mra_run_likelihood_local_async(self.h, self.stream(), C.c_void_p(self.summary.data_ptr())))
+
+    def likelihood_top_async(self):
+        """Sharded step 3 (after self.summary has been sum-reduced over the ranks): replicated top levels."""
+        self.check(self.lib.mra_run_likelihood_top_async(self.h, self.stream(), C.c_void_p(self.summary.data_ptr())))
 
     def fetch_likelihood(self):
         out = (C.c_double * 2)()
@@ -95,15 +130,30 @@ class DeviceSession(object):
         return float(out[0]), float(out[1])
 
     def predict(self):
+        if self.shard_level:
+            import torch
+            out = torch.empty(2, self.N, dtype=torch.float64, device=self.dev)
+            self.predict_dev(out[0], out[1], reduce=True)
+            host = out.cpu().numpy()
+            self.fetch_likelihood()                           # surfaces a non-SPD status like the plain path
+            return host[0].copy(), host[1].copy()
         mean = np.empty(self.N)
         sd = np.empty(self.N)
         self.check(self.lib.mra_run_predict(self.h, self.stream(), _dptr(mean), _dptr(sd)))
         return mean, sd
 
-    def predict_dev(self, mean_t=None, sd_t=None):
+    def predict_dev(self, mean_t=None, sd_t=None, reduce=False):
+        """Results into device tensors (caller's order).  Sharded: each rank fills its own rows and zeros
+        elsewhere; reduce=True sum-reduces them so every rank holds all N results."""
         pm = C.c_void_p(mean_t.data_ptr()) if mean_t is not None else None
         ps = C.c_void_p(sd_t.data_ptr()) if sd_t is not None else None
         self.check(self.lib.mra_run_predict_dev(self.h, self.stream(), pm, ps))
+        if reduce and self.shard_level:
+            import torch.distributed as dist
+            if mean_t is None or sd_t is None:
+                raise ValueError("reduce=True needs caller-owned output tensors")
+            dist.all_reduce(mean_t, group=self.group)
+            dist.all_reduce(sd_t, group=self.group)
 
     # ---- counters
     def launches(self):

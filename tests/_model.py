@@ -32,7 +32,10 @@ def cov_fn(family, l, sig):
     raise ValueError(family)
 
 
-def model_run(st, locs, obs, family, l, sig, R, want_predict=True, keep=False):
+def model_run(st, locs, obs, family, l, sig, R, want_predict=True, keep=False, shard=None):
+    """shard = (s, role, allreduce): emulate one rank of a sharded run (pymra_b200/shard.py): only nodes with
+    role != 0 are processed, the summaries of the level-s nodes are exchanged with `allreduce(array)` (in-place
+    sum over ranks) and the outputs of predict are zero outside this rank's rows and reduced the same way."""
     cov, c0 = cov_fn(family, l, sig)
     r = st.r
     X = np.asarray(locs, dtype=np.float64).reshape(st.N, st.d)[st.perm]
@@ -42,6 +45,7 @@ def model_run(st, locs, obs, family, l, sig, R, want_predict=True, keep=False):
     nn = st.n_nodes
     Lk = [None] * nn     # chol of conditional knot covariance (reference kInv)
     out = {}
+    s_lvl, role, allreduce = shard if shard is not None else (0, np.ones(nn, dtype=np.int8), None)
 
     def rng(n):
         s = int(st.node_row_start[n])
@@ -50,7 +54,7 @@ def model_run(st, locs, obs, family, l, sig, R, want_predict=True, keep=False):
     # ---- prior, top-down
     for m in range(st.depth + 1):
         for n in st.nodes_at(m):
-            if st.node_kind[n] != KIND_INTERNAL:
+            if st.node_kind[n] != KIND_INTERNAL or not role[n]:
                 continue
             K = st.knot_rows[st.node_knot_off[n]: st.node_knot_off[n] + r]
             VK = V[K, : m * r]
@@ -69,7 +73,7 @@ def model_run(st, locs, obs, family, l, sig, R, want_predict=True, keep=False):
     leafstate = {}
     for n in range(nn):
         kind = st.node_kind[n]
-        if kind == KIND_INTERNAL:
+        if kind == KIND_INTERNAL or not role[n]:
             continue
         m = int(st.node_level[n])
         rows = rng(n)
@@ -100,8 +104,24 @@ def model_run(st, locs, obs, family, l, sig, R, want_predict=True, keep=False):
     G = [None] * nn
     g = [None] * nn
     for m in range(st.depth, -1, -1):
+        if s_lvl and m == s_lvl - 1:
+            # exchange: slot per level-s node = [[At, wt], [wt^T, u]] (W x W) followed by d
+            lo, hi = int(st.level_off[s_lvl]), int(st.level_off[s_lvl + 1])
+            Kv = s_lvl * r
+            W = Kv + 1
+            buf = np.zeros((hi - lo, W * W + 1))
+            for c in range(lo, hi):
+                if role[c] != 1:
+                    continue
+                S = np.zeros((W, W))
+                S[:Kv, :Kv] = At[c]; S[:Kv, Kv] = wt[c]; S[Kv, :Kv] = wt[c]; S[Kv, Kv] = uu[c]
+                buf[c - lo, :W * W] = S.ravel(); buf[c - lo, W * W] = dd[c]
+            allreduce(buf)
+            for c in range(lo, hi):
+                S = buf[c - lo, :W * W].reshape(W, W)
+                At[c] = S[:Kv, :Kv].copy(); wt[c] = S[:Kv, Kv].copy(); uu[c] = float(S[Kv, Kv]); dd[c] = float(buf[c - lo, W * W])
         for n in st.nodes_at(m):
-            if st.node_kind[n] != KIND_INTERNAL:
+            if st.node_kind[n] != KIND_INTERNAL or not role[n]:
                 continue
             cs, cc = int(st.node_child_start[n]), int(st.node_child_count[n])
             A = sum(At[c] for c in range(cs, cs + cc))
@@ -127,6 +147,10 @@ def model_run(st, locs, obs, family, l, sig, R, want_predict=True, keep=False):
     mean = np.zeros(st.N)
     var = np.zeros(st.N)
     Vt = V
+    emit = np.ones(st.N, dtype=bool)
+    if s_lvl:
+        from pymra_b200.shard import owned_rows
+        emit = owned_rows(st, role)
     for n, ls in leafstate.items():
         m = int(st.node_level[n])
         rows = rng(n)
@@ -144,7 +168,7 @@ def model_run(st, locs, obs, family, l, sig, R, want_predict=True, keep=False):
             var[rows] = resid
     for m in range(st.depth, -1, -1):
         for n in st.nodes_at(m):
-            if st.node_kind[n] != KIND_INTERNAL:
+            if st.node_kind[n] != KIND_INTERNAL or not role[n]:
                 continue
             rows = rng(n)
             t = solve_triangular(Lp[n], Vt[rows, m * r:(m + 1) * r].T, lower=True).T
@@ -153,7 +177,13 @@ def model_run(st, locs, obs, family, l, sig, R, want_predict=True, keep=False):
             Vt[rows, : m * r] -= t @ G[n]
     inv = np.empty(st.N, dtype=np.int64)
     inv[st.perm] = np.arange(st.N)
+    sd = np.sqrt(np.maximum(var, 0.0))
+    if s_lvl:
+        mean = np.where(emit, mean, 0.0); sd = np.where(emit, sd, 0.0); var = np.where(emit, var, 0.0)
+        res = np.stack((mean, sd, var))
+        allreduce(res)
+        mean, sd, var = res
     out["mean"] = mean[inv]
-    out["sd"] = np.sqrt(np.maximum(var, 0.0))[inv]
+    out["sd"] = sd[inv]
     out["var"] = var[inv]
     return out

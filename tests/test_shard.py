@@ -1,0 +1,95 @@
+"""Host-side logic of the multi-GPU subtree sharding (pymra_b200/shard.py), on CPU:
+  * the plan partitions the level-s subtrees and the output rows exactly once over the ranks;
+  * a world_size-2 gloo run of the NumPy blueprint of the device algorithm (tests/_model.py) with the
+    summary exchange reproduces the unsharded likelihood / mean / sd (the same three-step protocol the
+    CUDA path uses: local pass -> all-reduce of summaries -> replicated top)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from _util import load_golden, structure_for
+
+from pymra_b200.shard import (ROLE_MINE, ROLE_OTHER, ROLE_TOP, ROLE_TOP_EMIT, choose_shard_level, owned_rows,
+                              plan_shards, summary_width)
+
+
+@pytest.mark.parametrize("name", ["g96_m32_r16", "g125_m32_r16", "ka4_large_serial", "g30_kmeans"])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_plan_partitions_subtrees_and_rows(name, world):
+    st = structure_for(load_golden(name))
+    s = choose_shard_level(st, world)
+    if s is None:
+        pytest.skip("tree too shallow to shard %d ways" % world)
+    lo, hi = int(st.level_off[s]), int(st.level_off[s + 1])
+    assert hi - lo >= world and (s == 1 or int(st.level_off[s]) - int(st.level_off[s - 1]) < world)
+    cover = np.zeros(st.N, dtype=int)
+    owners = np.zeros(hi - lo, dtype=int)
+    for rank in range(world):
+        s2, role, owner = plan_shards(st, world, rank)
+        assert s2 == s and len(role) == st.n_nodes
+        assert np.all(role[:lo] == (ROLE_TOP_EMIT if rank == 0 else ROLE_TOP))
+        assert set(np.unique(role[lo:])) <= {ROLE_MINE, ROLE_OTHER}
+        owners += (role[lo:hi] == ROLE_MINE)
+        # descendants inherit the role of their level-s ancestor
+        for n in range(hi, st.n_nodes):
+            assert role[n] == role[st.node_parent[n]]
+        cover += owned_rows(st, role)
+    assert np.all(owners == 1)
+    assert np.all(cover == 1)
+    assert summary_width(st, s) == s * st.r + 1
+
+
+def _free_port():
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        return so.getsockname()[1]
+
+
+def _worker(rank, world, port, name, q):
+    import torch
+    import torch.distributed as dist
+    from _model import model_run
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = load_golden(name)
+    st = structure_for(g)
+    s, role, _ = plan_shards(st, world, rank)
+
+    def allreduce(a):
+        t = torch.from_numpy(a)
+        dist.all_reduce(t)
+
+    res = model_run(st, g["locs"], g["obs"], str(g["family"]), float(g["l"]), float(g["sig"]), float(g["R"]),
+                    shard=(s, role, allreduce))
+    q.put((rank, s, res["lik"], res["mean"], res["sd"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,world", [("g96_m32_r16", 2), ("g125_m32_r16", 2)])
+def test_gloo_sharded_model_matches_unsharded(name, world):
+    import torch.multiprocessing as mp
+    from _model import model_run
+    g = load_golden(name)
+    st = structure_for(g)
+    ref = model_run(st, g["locs"], g["obs"], str(g["family"]), float(g["l"]), float(g["sig"]), float(g["R"]))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(rk, world, port, name, q)) for rk in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, s, lik, mean, sd in got:
+        assert s >= 1
+        assert abs(lik - ref["lik"]) <= 1e-11 * abs(ref["lik"])
+        assert np.max(np.abs(mean - ref["mean"])) <= 1e-10
+        assert np.max(np.abs(sd - ref["sd"])) <= 1e-10
+    # and the reference itself
+    assert abs(got[0][2] - float(g["lik"])) <= 1e-9 * abs(float(g["lik"]))
