@@ -15,14 +15,19 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 namespace {
 
+// Legacy NumPy MT19937 (mtrand's rk_state): key[624] + pos.  Outputs are produced 624 at a time,
+// already tempered, so the hot loops below read a plain buffer.
 struct MT {
   uint32_t key[624];
   int pos;
+  uint32_t out[624];
+  bool out_valid = false;
   void gen() {
     const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, MA = 0x9908b0dfu;
     int kk;
@@ -38,28 +43,66 @@ struct MT {
     y = (key[623] & UP) | (key[0] & LO);
     key[623] = key[396] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MA);
     pos = 0;
+    out_valid = false;
+  }
+  void temper_all() {
+    for (int i = 0; i < 624; ++i) {
+      uint32_t y = key[i];
+      y ^= (y >> 11);
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= (y >> 18);
+      out[i] = y;
+    }
+    out_valid = true;
+  }
+  // makes out[pos .. 624) readable; returns how many outputs are available (>= 1)
+  inline int avail() {
+    if (pos >= 624) gen();
+    if (!out_valid) temper_all();
+    return 624 - pos;
   }
   inline uint32_t next32() {
-    if (pos >= 624) gen();
-    uint32_t y = key[pos++];
-    y ^= (y >> 11);
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= (y >> 18);
-    return y;
+    avail();
+    return out[pos++];
   }
-  inline uint32_t interval(uint32_t max) {   // uniform on [0, max], max <= 0xffffffff
-    if (max == 0) return 0;
+  static inline uint32_t smear(uint32_t max) {
     uint32_t mask = max;
     mask |= mask >> 1;
     mask |= mask >> 2;
     mask |= mask >> 4;
     mask |= mask >> 8;
     mask |= mask >> 16;
+    return mask;
+  }
+  inline uint32_t interval(uint32_t max) {   // uniform on [0, max], max <= 0xffffffff (legacy rk_interval)
+    if (max == 0) return 0;
+    const uint32_t mask = smear(max);
     uint32_t v;
     while ((v = (next32() & mask)) > max) {
     }
     return v;
+  }
+  // jb[i] = interval(i) for i = hi, hi-1, ..., 1 -- the draw sequence of the legacy Fisher-Yates shuffle.
+  // Same stream consumption as calling interval() one by one; the rejection loop is branch-free inside a
+  // power-of-two segment of i (the mask is constant there): a rejected value is simply overwritten.
+  void shuffle_draws(int32_t* jb, int64_t hi) {
+    int64_t i = hi;
+    while (i >= 1) {
+      const uint32_t mask = smear((uint32_t)i);
+      const int64_t lo = (int64_t)(mask >> 1) + 1;          // smallest i with this mask
+      while (i >= lo) {
+        int n = avail();
+        const uint32_t* o = out + pos;
+        int used = 0;
+        while (used < n && i >= lo) {
+          const uint32_t v = o[used++] & mask;
+          jb[i] = (int32_t)v;
+          i -= (v <= (uint32_t)i);
+        }
+        pos += used;
+      }
+    }
   }
 };
 
@@ -67,108 +110,164 @@ struct Rec {
   int level, parent, kind;
   int64_t row_start, row_count;
   int first_child, n_child;
-  int64_t knot_off;   // into knots_global
+  int64_t knot_off;   // into knot_tree_row / kinds_local
+};
+
+// An ancestor's (or the node's own) knot lying inside a node: local position and knot slot.
+struct KEnt {
+  int32_t pos, id;
+};
+
+template <class T>
+struct RawBuf {   // uninitialised, reused across calls (first-touch page faults are paid once per size)
+  T* p = nullptr;
+  size_t cap = 0;
+  T* get(size_t n) {
+    if (n > cap) {
+      std::free(p);
+      p = static_cast<T*>(std::malloc(sizeof(T) * n));
+      cap = p ? n : 0;
+    }
+    return p;
+  }
+  ~RawBuf() { std::free(p); }
+};
+
+struct Pool {
+  RawBuf<int32_t> rows[2], scratch, draws, perm;
+  RawBuf<double> xs[2], ys[2];
+  RawBuf<uint8_t> code, slot_of;
+  RawBuf<uint64_t> bits;
+  size_t bits_n = 0;
 };
 
 struct Builder {
-  const double* locs;
   int64_t N;
   int r, J, critDepth;
   MT rng;
-  // ping-pong level buffers
-  std::vector<int32_t> rows[2];
-  std::vector<double> xs[2], ys[2];
-  std::vector<uint8_t> nk[2];
-  std::vector<int32_t> scratch;       // permutation work array
-  std::vector<uint8_t> code;
+  int32_t* rows[2];
+  double *xs[2], *ys[2];
+  int32_t *scratch, *draws, *perm;
+  uint8_t *code, *slot_of;
+  uint64_t* bits;                        // tracked-position bitmap of the reverse selection (all zero between nodes)
+  static constexpr int64_t REVERSE_MIN = 32768;
   std::vector<Rec> rec;
-  std::vector<int64_t> knots_global;  // r per internal node, in reference knot order
-  std::vector<int32_t> kinds_local;   // r per internal node
-  std::vector<int32_t> perm;
+  std::vector<int32_t> knot_tree_row;    // r per internal node, in reference knot order; resolved at the leaves
+  std::vector<int32_t> kinds_local;      // r per internal node
   int status = 0;
 
-  // node occupying [s, e) of buffer b
-  void visit(int parent, int level, int64_t s, int64_t e, int b, int levels_left) {
+  // a[0..r) of np.random.permutation(n) on the legacy stream (== np.random.choice(arange(n), r, False))
+  void first_r_of_permutation(int64_t n, int32_t* out) {
+    if (n < REVERSE_MIN || r > 256) {
+      // Small node: the work array is cache resident, run the legacy shuffle as it is.
+      int32_t* a = scratch;
+      int32_t* jb = draws;
+      rng.shuffle_draws(jb, n - 1);
+      for (int64_t i = 0; i < n; ++i) a[i] = (int32_t)i;
+      for (int64_t i = n - 1; i >= 1; --i) {
+        const int32_t j = jb[i];
+        const int32_t t = a[i];
+        a[i] = a[j];
+        a[j] = t;
+      }
+      for (int p = 0; p < r; ++p) out[p] = a[p];
+      return;
+    }
+    // Large node: only a[0..r) of the shuffled arange is needed.  The draws j_i (i = n-1 .. 1) are
+    // generated in the legacy order and buffered; steps i >= r are then undone in reverse time order
+    // while tracking where the values that end up in positions < r came from (a bitmap of the r tracked
+    // positions stays cache resident, the 4n-byte work array is never touched at random); the last
+    // r-1 steps only permute the prefix and are replayed forward.
+    int32_t* jb = scratch;                             // jb[i] = j_i
+    rng.shuffle_draws(jb, n - 1);
+    int32_t key[256];
+    for (int p = 0; p < r; ++p) {
+      key[p] = p;
+      bits[p >> 6] |= 1ull << (p & 63);
+      slot_of[p] = (uint8_t)p;
+    }
+    for (int64_t i = r; i < n; ++i) {
+      const int32_t j = jb[i];
+      if ((bits[j >> 6] >> (j & 63)) & 1ull) {
+        if (j == i) continue;
+        const uint8_t sl = slot_of[j];
+        bits[j >> 6] &= ~(1ull << (j & 63));
+        bits[i >> 6] |= 1ull << (i & 63);
+        slot_of[i] = sl;
+        key[sl] = (int32_t)i;
+      }
+    }
+    for (int p = 0; p < r; ++p) {
+      out[p] = key[p];                                 // initial array is arange: value == position
+      bits[key[p] >> 6] &= ~(1ull << (key[p] & 63));
+    }
+    for (int i = r - 1; i >= 1; --i) {
+      const int32_t j = jb[i];
+      const int32_t t = out[i];
+      out[i] = out[j];
+      out[j] = t;
+    }
+  }
+
+  // node occupying [s, e) of buffer b; kp = knots of its ancestors lying inside it (sorted by position),
+  // (sx, sy) = column sums of its locations accumulated in row order from 0.0 (np.mean's order)
+  void visit(int parent, int level, int64_t s, int64_t e, int b, int levels_left, const std::vector<KEnt>& kp,
+             double sx, double sy) {
     if (status) return;
     const int me = (int)rec.size();
     rec.push_back(Rec{level, parent, MRA_NODE_LEAF, s, e - s, -1, 0, -1});
     const int64_t n = e - s;
-    const int32_t* R = rows[b].data() + s;
-    const double* X = xs[b].data() + s;
-    const double* Y = ys[b].data() + s;
-    uint8_t* F = nk[b].data() + s;
-    int64_t n_nk = 0;
-    for (int64_t i = 0; i < n; ++i) n_nk += F[i];
+    const int32_t* R = rows[b] + s;
+    const double* X = xs[b] + s;
+    const double* Y = ys[b] + s;
+    const int64_t n_nk = n - (int64_t)kp.size();
     const bool internal = levels_left > 0 && n_nk > std::max(r, J);
     if (!internal) {
-      std::memcpy(perm.data() + s, R, sizeof(int32_t) * n);
+      std::memcpy(perm + s, R, sizeof(int32_t) * n);
+      for (const KEnt& k : kp) knot_tree_row[k.id] = (int32_t)(s + k.pos);
       return;
     }
     if (n_nk <= 100 || n <= 100) {   // KMeans knot / split paths: not handled natively
       status = 1;
       return;
     }
-    // ---- knots: permutation(n_nk)[:r] mapped through the not-knot list, sorted
-    int32_t* a = scratch.data();
-    for (int64_t i = 0; i < n_nk; ++i) a[i] = (int32_t)i;
-    {
-      // Fisher-Yates from the top; the draws do not depend on the array, so they are generated
-      // LA steps ahead (same order, same stream) and their targets prefetched.
-      constexpr int LA = 64;
-      uint32_t jq[LA];
-      int64_t gen_i = n_nk - 1;
-      for (int s0 = 0; s0 < LA && gen_i >= 1; ++s0, --gen_i) {
-        jq[s0] = rng.interval((uint32_t)gen_i);
-        __builtin_prefetch(&a[jq[s0]], 1);
-      }
-      int slot = 0;
-      for (int64_t i = n_nk - 1; i >= 1; --i) {
-        const uint32_t j = jq[slot];
-        if (gen_i >= 1) {
-          jq[slot] = rng.interval((uint32_t)gen_i);
-          __builtin_prefetch(&a[jq[slot]], 1);
-          --gen_i;
-        }
-        slot = (slot + 1 == LA) ? 0 : slot + 1;
-        const int32_t t = a[i];
-        a[i] = a[j];
-        a[j] = t;
-      }
-    }
-    std::vector<int32_t> pick(a, a + r);
-    std::sort(pick.begin(), pick.end());
-    // map candidate index -> local row id
+    // ---- knots: sorted permutation(n_nk)[:r], candidate index -> local position by skipping the
+    // ancestors' knots (select on the sorted kp list instead of a scan of the node)
+    int32_t pick[256];
+    first_r_of_permutation(n_nk, pick);
+    std::sort(pick, pick + r);
     rec[me].kind = MRA_NODE_INTERNAL;
-    rec[me].knot_off = (int64_t)knots_global.size();
+    rec[me].knot_off = (int64_t)kinds_local.size();
+    std::vector<KEnt> mk;             // kp merged with the new knots, sorted by position
+    mk.reserve(kp.size() + r);
     {
-      int64_t c = 0;
-      int p = 0;
-      for (int64_t i = 0; i < n && p < r; ++i) {
-        if (F[i]) {
-          if (c == pick[p]) {
-            kinds_local.push_back((int32_t)i);
-            knots_global.push_back(R[i]);
-            F[i] = 0;
-            ++p;
-          }
-          ++c;
+      size_t j = 0;
+      for (int t = 0; t < r; ++t) {
+        int32_t pos = pick[t] + (int32_t)j;
+        while (j < kp.size() && kp[j].pos <= pos) {
+          mk.push_back(kp[j]);
+          ++j;
+          ++pos;
         }
+        const int32_t id = (int32_t)kinds_local.size();
+        kinds_local.push_back(pos);
+        knot_tree_row.push_back(-1);
+        mk.push_back(KEnt{pos, id});
       }
+      for (; j < kp.size(); ++j) mk.push_back(kp[j]);
     }
-    // ---- quadrant split by column means (sequential sums, as NumPy reduces axis 0 of an (n,2) array)
-    double sx = 0.0, sy = 0.0;
-    for (int64_t i = 0; i < n; ++i) {
-      sx += X[i];
-      sy += Y[i];
-    }
+    // ---- quadrant split by column means (MRANode.py:232-239)
     const double mx = sx / (double)n, my = sy / (double)n;
-    int64_t cnt[4] = {0, 0, 0, 0};
-    uint8_t* C = code.data() + s;
+    uint8_t* C = code + s;
+    int64_t nx = 0, ny = 0, nxy = 0;
     for (int64_t i = 0; i < n; ++i) {
-      uint8_t c = (uint8_t)((X[i] <= mx ? 0 : 2) + (Y[i] <= my ? 0 : 1));
-      C[i] = c;
-      ++cnt[c];
+      const int gx = X[i] > mx, gy = Y[i] > my;     // !(x <= mx): NaN-free inputs
+      C[i] = (uint8_t)(2 * gx + gy);
+      nx += gx;
+      ny += gy;
+      nxy += gx & gy;
     }
+    const int64_t cnt[4] = {n - nx - ny + nxy, ny - nxy, nx - nxy, nxy};
     for (int c = 0; c < 4; ++c)
       if (cnt[c] == 0) {
         status = 1;   // the reference would build an empty child here; not handled natively
@@ -178,18 +277,42 @@ struct Builder {
     off[0] = s;
     for (int c = 1; c < 4; ++c) off[c] = off[c - 1] + cnt[c - 1];
     const int nb = b ^ 1;
+    std::vector<KEnt> ckp[4];
+    double csx[4] = {0.0, 0.0, 0.0, 0.0}, csy[4] = {0.0, 0.0, 0.0, 0.0};
     {
       int64_t w[4] = {off[0], off[1], off[2], off[3]};
-      int32_t* R2 = rows[nb].data();
-      double* X2 = xs[nb].data();
-      double* Y2 = ys[nb].data();
-      uint8_t* F2 = nk[nb].data();
-      for (int64_t i = 0; i < n; ++i) {
-        const int64_t d = w[C[i]]++;
-        R2[d] = R[i];
-        X2[d] = X[i];
-        Y2[d] = Y[i];
-        F2[d] = F[i];
+      int32_t* R2 = rows[nb];
+      double* X2 = xs[nb];
+      double* Y2 = ys[nb];
+      size_t q = 0;
+      int64_t next_k = mk.empty() ? n : mk[0].pos;
+      int64_t i = 0;
+      while (i < n) {
+        const int64_t stop = std::min(next_k, n);
+        for (; i < stop; ++i) {                      // plain stretch between two knots
+          const int c = C[i];
+          const int64_t d = w[c]++;
+          R2[d] = R[i];
+          const double x = X[i], y = Y[i];
+          X2[d] = x;
+          Y2[d] = y;
+          csx[c] += x;
+          csy[c] += y;
+        }
+        if (i < n) {                                 // i is a knot position: same move, remember where it went
+          const int c = C[i];
+          const int64_t d = w[c]++;
+          R2[d] = R[i];
+          const double x = X[i], y = Y[i];
+          X2[d] = x;
+          Y2[d] = y;
+          csx[c] += x;
+          csy[c] += y;
+          ckp[c].push_back(KEnt{(int32_t)(d - off[c]), mk[q].id});
+          ++q;
+          next_k = q < mk.size() ? mk[q].pos : n;
+          ++i;
+        }
       }
     }
     const bool fork = level == critDepth;
@@ -199,9 +322,7 @@ struct Builder {
     for (int c = 0; c < 4; ++c) {
       if (fork) rng = saved;
       if (c == 0) rec[me].first_child = (int)rec.size();
-      int child = (int)rec.size();
-      (void)child;
-      visit(me, level + 1, off[c], off[c] + cnt[c], nb, levels_left - 1);
+      visit(me, level + 1, off[c], off[c] + cnt[c], nb, levels_left - 1, ckp[c], csx[c], csy[c]);
       if (status) return;
     }
     if (fork) rng = saved;
@@ -220,8 +341,9 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
                            int64_t* knot_rows, int32_t* kinds_local, int64_t* n_knot_rows_out, int64_t* perm,
                            int32_t* dfs_index) {
   if (!locs || n_locs <= 0 || n_locs >= (int64_t(1) << 31) || r < 1 || !mt_key || !mt_pos) return MRA_ERR_ARG;
+  if (r > 256) return MRA_BUILD_UNSUPPORTED;
+  static thread_local Pool pool;
   Builder B;
-  B.locs = locs;
   B.N = n_locs;
   B.r = r;
   B.J = J;
@@ -230,21 +352,35 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
   B.rng.pos = *mt_pos;
   const int64_t N = n_locs;
   for (int b = 0; b < 2; ++b) {
-    B.rows[b].resize(N);
-    B.xs[b].resize(N);
-    B.ys[b].resize(N);
-    B.nk[b].resize(N);
+    B.rows[b] = pool.rows[b].get(N);
+    B.xs[b] = pool.xs[b].get(N);
+    B.ys[b] = pool.ys[b].get(N);
   }
-  B.scratch.resize(N);
-  B.code.resize(N);
-  B.perm.resize(N);
+  B.scratch = pool.scratch.get(N);
+  B.draws = pool.draws.get(std::min<int64_t>(N, Builder::REVERSE_MIN) + 1);
+  B.perm = pool.perm.get(N);
+  B.code = pool.code.get(N);
+  B.slot_of = pool.slot_of.get(N);
+  {
+    const size_t nb = (size_t)(N + 63) / 64 + 1;
+    const bool fresh = nb > pool.bits.cap;
+    B.bits = pool.bits.get(nb);
+    if (B.bits && (fresh || pool.bits_n < nb)) std::memset(B.bits, 0, sizeof(uint64_t) * pool.bits.cap);
+    pool.bits_n = pool.bits.cap;
+  }
+  if (!B.rows[0] || !B.rows[1] || !B.xs[0] || !B.xs[1] || !B.ys[0] || !B.ys[1] || !B.scratch || !B.draws ||
+      !B.perm || !B.code || !B.slot_of || !B.bits)
+    return MRA_ERR_NOMEM;
+  double sx = 0.0, sy = 0.0;
   for (int64_t i = 0; i < N; ++i) {
     B.rows[0][i] = (int32_t)i;
-    B.xs[0][i] = locs[2 * i];
-    B.ys[0][i] = locs[2 * i + 1];
-    B.nk[0][i] = 1;
+    const double x = locs[2 * i], y = locs[2 * i + 1];
+    B.xs[0][i] = x;
+    B.ys[0][i] = y;
+    sx += x;
+    sy += y;
   }
-  B.visit(-1, 0, 0, N, 0, M);
+  B.visit(-1, 0, 0, N, 0, M, std::vector<KEnt>(), sx, sy);
   if (B.status) return MRA_BUILD_UNSUPPORTED;
   const int nn = (int)B.rec.size();
   if (nn > max_nodes) return MRA_ERR_NOMEM;
@@ -258,8 +394,6 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
     std::vector<int> next(count.begin(), count.end() - 1);
     for (int i = 0; i < nn; ++i) newid[i] = next[B.rec[i].level]++;
   }
-  std::vector<int32_t> inv(N);
-  for (int64_t i = 0; i < N; ++i) inv[B.perm[i]] = (int32_t)i;
   int64_t koff = 0;
   // internal nodes must receive knot offsets in BFS order (like the Python builder)
   std::vector<int> order(nn);
@@ -277,7 +411,7 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
     if (rc.kind == MRA_NODE_INTERNAL) {
       node_knot_off[id] = koff;
       for (int k = 0; k < r; ++k) {
-        knot_rows[koff + k] = inv[B.knots_global[rc.knot_off + k]];
+        knot_rows[koff + k] = B.knot_tree_row[rc.knot_off + k];
         kinds_local[koff + k] = B.kinds_local[rc.knot_off + k];
       }
       koff += r;

@@ -8,7 +8,8 @@ import pymra_b200.MRATools as mt
 from pymra_b200.structure import build_structure, build_structure_native
 
 CASES = [(40, 40, 8, 2, 5), (50, 50, 16, 2, 6), (33, 47, 5, 2, 7), (64, 64, 8, 3, 8), (96, 96, 16, 3, 12),
-         (125, 125, 16, 4, 5), (201, 157, 32, 3, 9), (128, 128, 64, 2, 1), (300, 300, 16, 5, 2)]
+         (125, 125, 16, 4, 5), (201, 157, 32, 3, 9), (128, 128, 64, 2, 1), (300, 300, 16, 5, 2),
+         (400, 380, 64, 3, 4), (512, 512, 128, 2, 13)]   # the last two take the reverse-traced selection on 2 levels
 
 
 def same(a, b):
@@ -58,7 +59,7 @@ def test_native_on_scattered_points():
 
 def test_legacy_choice_clone_against_numpy():
     """np.random.choice(np.arange(n), r, replace=False) for the root == sorted knots of a depth-1 tree."""
-    for seed, n, r in [(1, 20, 3), (2, 37, 8), (11, 64, 16), (5, 101, 64)]:
+    for seed, n, r in [(1, 20, 3), (2, 37, 8), (11, 64, 16), (5, 101, 64), (7, 450, 64), (9, 300, 128)]:
         locs = mt.genLocations2d(n)
         np.random.seed(seed)
         want = np.sort(np.random.choice(np.arange(n * n), size=r, replace=False))
