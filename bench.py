@@ -248,6 +248,7 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         if i > 0:
             t_e2e.append(max_over_ranks(time.time() - t0))
+            e2e_breakdown = {k: round(v, 4) for k, v in tree.timings.items()}
         del tree
     e2e_value = 1.0 / float(np.mean(t_e2e))
     clocks = sampler.stop() if sampler is not None else None
@@ -304,7 +305,7 @@ def run_ours(args, rank, world, local_rank):
                     "predict_locations_per_s": e2e_value * N, "host_structure_s": t_struct,
                     "what": "MRATree(locs, r, cov, obs, R, M) + getLikelihood() + predict(), host numpy in/out, "
                             "fresh knot draw per construction (reference RNG semantics)",
-                    "likelihood": lik_e2e},
+                    "likelihood": lik_e2e, "host_breakdown_s": e2e_breakdown},
             "gpu_launches": int(launches * args.steps * world),
             "roofline": roofline, "kernels": kern, "cpu_baseline": cb, "clocks": clocks,
             "algorithmic_flops": {"likelihood": f_lik, "predict": f_pred},

@@ -14,6 +14,7 @@ RNG state, whole subtrees are sharded over the ranks' GPUs (pymra_b200/shard.py)
 the full likelihood and predictions.
 """
 import logging
+import time
 
 import numpy as np
 
@@ -73,6 +74,8 @@ class _Root(object):
 class MRATree(object):
 
     def __init__(self, locs, r, cov, obs, R, M=-1, J=-1, critDepth=-1, verbose=True, device=None, group=None):
+        t0 = time.perf_counter()
+        self.timings = {}          # host-side wall-clock breakdown of this construction (seconds)
         self.locs = locs
         self.d = np.shape(self.locs)[1]
         N = len(locs)
@@ -96,11 +99,17 @@ class MRATree(object):
         logger.debug("mode: %s" % ("serial" if critDepth > self.M else "parallel"))
 
         locs_c = np.ascontiguousarray(locs, dtype=np.float64).reshape(N, self.d)
+        t1 = time.perf_counter()
         self._structure = build_structure(locs_c, r, M, J, critDepth)
+        t2 = time.perf_counter()
         self._session = DeviceSession(self._structure, locs_c, obs_arr, want_predict=True, device=device, group=group)
+        t3 = time.perf_counter()
         self._mom = None
         self._evaluate()
         self.root = _Root(self)
+        t4 = time.perf_counter()
+        self.timings.update(args_and_cov=t1 - t0, structure=t2 - t1, session_plan_upload=t3 - t2,
+                            likelihood=t4 - t3, **self._session.timings)
 
     # ---- plumbing
     def _evaluate(self):
@@ -110,8 +119,10 @@ class MRATree(object):
 
     def _moments(self):
         if self._mom is None:
+            t0 = time.perf_counter()
             mean, sd = self._session.predict()
             self._mom = (np.matrix(mean.reshape(-1, 1)), sd * sd, sd)
+            self.timings["predict"] = time.perf_counter() - t0
         return self._mom
 
     def _debug_fetch(self, what, node=0, count=None):

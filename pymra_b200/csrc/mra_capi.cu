@@ -29,7 +29,7 @@ struct Arena {
 
 struct Layout {
   size_t nodes, knot_rows, obs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
-      mean, var, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks;
+      mean, var, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks, ltiles;
   size_t total;
 };
 
@@ -52,6 +52,7 @@ struct mra_handle {
   std::vector<std::vector<int4>> tiles_at;     // 64-row tiles of internal nodes per level (predict pass)
   std::vector<std::vector<int4>> ptiles_at;    // prior pass: the same plus gathered knot tiles (sharded runs)
   std::vector<int> gather_rows;                // row ids of the gathered tiles
+  std::vector<int4> leaf_tiles;                // 64-row tiles of leaves / orphans (fused predict pass)
   std::vector<int2> emit_chunks;               // row ranges whose results this rank emits
   // subtree sharding (mra_set_shard): role per node, 0 = another rank's, 1 = mine, 2 = replicated top,
   // 3 = replicated top whose rows this rank emits
@@ -152,7 +153,7 @@ size_t smem_plain() { return GS; }
 size_t smem_factor(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + r); }
 size_t smem_predict(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;
-  return GS + sizeof(double) * ((size_t)TB * ldT);
+  return GS + sizeof(double) * ((size_t)TB * ldT + 2 * TB) + sizeof(int) * MAX_LEVELS;
 }
 
 // Kernels are instantiated for VEC = 2 (16-byte cp.async, even r) and VEC = 1 (odd r).
@@ -180,8 +181,7 @@ cudaError_t configure_vec(int r) {
   SET_(k_leaf_solve<V_>, smem_solve());
   SET_(k_assemble_A<V_>, smem_plain());
   SET_(k_node_factor<V_>, smem_factor(r));
-  SET_(k_leaf_apply<V_>, smem_plain());
-  SET_(k_predict_level<V_>, smem_predict(r));
+  SET_(k_predict_fused<V_>, smem_predict(r));
 #undef SET_
   return cudaSuccess;
 }
@@ -352,22 +352,16 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
   if (!h->pred_done) {
     const int nleaf = (int)h->leaves.size();
     const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off);
-    LAUNCH("resid_var", k_resid_var<<<nleaf, 256, 0, st>>>(c, leaf_list));
     if (h->max_leaf_obs > 0) {
       const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
       dim3 g1(nleaf, nbr * nbo);
       MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<g1, NT, smem_gram(), st>>>(c, leaf_list, 1)));
       dim3 g2(nleaf, nbr);
       MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", k_leaf_solve<V_><<<g2, NT, smem_solve(), st>>>(c, leaf_list, 1)));
-      dim3 g3(nleaf, nbr * ((h->max_leaf_W + TB - 1) / TB));
-      MRA_FOR_VEC(h, LAUNCH("leaf_apply", k_leaf_apply<V_><<<g3, NT, smem_plain(), st>>>(c, leaf_list)));
     }
-    for (int m = (int)h->internal_at.size() - 1; m >= 0; --m) {
-      const int ntile = (int)h->tiles_at[m].size();
-      if (!ntile) continue;
-      const int4* tiles = reinterpret_cast<const int4*>(h->ws + L.tiles + h->tiles_off[m]);
-      MRA_FOR_VEC(h, LAUNCH("predict_level", k_predict_level<V_><<<ntile, NT, smem_predict(r), st>>>(c, tiles, m)));
-    }
+    if (!h->leaf_tiles.empty())
+      MRA_FOR_VEC(h, LAUNCH("predict_fused", k_predict_fused<V_><<<(unsigned)h->leaf_tiles.size(), NT, smem_predict(r), st>>>(
+                                                 c, at<int4>(h, L.ltiles))));
     h->pred_done = true;   // V now holds the posterior-updated basis; results stay cached in mean/var
   }
   double* om = dev_mean ? dev_mean : at<double>(h, L.out_mean);
@@ -458,6 +452,10 @@ void build_lists(mra_handle* h) {
     h->tiles_at.pop_back();
     h->ptiles_at.pop_back();
   }
+  h->leaf_tiles.clear();
+  for (int n : h->leaves)
+    for (int64_t r0 = 0; r0 < h->row_count[n]; r0 += TB)
+      h->leaf_tiles.push_back(make_int4(n, (int)(h->row_start[n] + r0), (int)std::min<int64_t>(TB, h->row_count[n] - r0), 0));
 }
 
 }  // namespace
@@ -497,6 +495,7 @@ int mra_set_structure(mra_handle* h, const mra_structure* s) {
   if (s->dim != 1 && s->dim != 2) return fail(h, MRA_ERR_ARG, "dim must be 1 or 2");
   if (s->r < 1 || s->r > 128) return fail(h, MRA_ERR_ARG, "r must be in [1, 128] in this build");
   if (s->n_nodes < 1 || s->depth < 0) return fail(h, MRA_ERR_ARG, "empty tree");
+  if (s->depth >= MAX_LEVELS) return fail(h, MRA_ERR_ARG, "tree deeper than MAX_LEVELS in this build");
   h->N = s->n_locs;
   h->dim = s->dim;
   h->r = s->r;
@@ -591,7 +590,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
         if (h->kind[ch] == KIND_INTERNAL) fa += Waf * Waf * rr;
       add_work(h, "assemble_A", fa, 8.0 * Waf * Waf);
       add_work(h, "node_factor", 2.0 * rr * rr * rr / 3.0 + (Kv + 1) * rr * rr, 8.0 * (rr * rr + 2 * (Kv + 1) * rr));
-      add_work(h, "predict_level", nr * rr * rr + 2.0 * nr * rr * Kv + 4.0 * nr * rr, 8.0 * nr * (2 * Kv + rr + 4));
+      add_work(h, "predict_fused", nr * rr * rr + 2.0 * nr * rr * Kv + 4.0 * nr * rr, 8.0 * nr * rr);
     } else {
       d.obs_off = (int)h->obs_rows.size();
       if (d.kind == KIND_LEAF) {
@@ -620,10 +619,10 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       add_work(h, "leaf_solve", no * no * W, 8.0 * (2 * no * W + no * no / 2));
       add_work(h, "assemble_A", W * W * no, 8.0 * no * W);
       if (d.kind == KIND_LEAF) {
-        add_work(h, "resid_var", 2.0 * nl * Kv, 8.0 * nl * (Kv + 2));
+        add_work(h, "predict_fused", 2.0 * nl * Kv, 8.0 * nl * (Kv + 2));
         add_work(h, "leaf_gram_T", 2.0 * nl * no * Kv, 8.0 * ((nl + no) * Kv + nl * no));
         add_work(h, "leaf_solve_Q", nl * no * no, 8.0 * (2 * nl * no + no * no / 2));
-        add_work(h, "leaf_apply", 2.0 * nl * no * W + 2.0 * nl * no, 8.0 * (nl * no + no * W + 2 * nl * Kv));
+        add_work(h, "predict_fused", 2.0 * nl * no * W + 2.0 * nl * no, 8.0 * (nl * no + no * W));
       }
     }
   }
@@ -632,8 +631,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   h->flops_lik = h->flops_pred = 0.0;
   for (size_t i = 0; i < h->kname.size(); ++i) {
     const std::string& nm = h->kname[i];
-    const bool pred = nm == "resid_var" || nm == "leaf_gram_T" || nm == "leaf_solve_Q" || nm == "leaf_apply" ||
-                      nm == "predict_level" || nm == "unpermute";
+    const bool pred = nm == "leaf_gram_T" || nm == "leaf_solve_Q" || nm == "predict_fused" || nm == "unpermute";
     (pred ? h->flops_pred : h->flops_lik) += h->kflops[i];
   }
   // ---- arena layout
@@ -687,6 +685,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.ptiles = ar.take(std::max<size_t>(256, po));
   L.gather = ar.take(std::max<size_t>(256, sizeof(int) * h->gather_rows.size()));
   L.chunks = ar.take(std::max<size_t>(256, sizeof(int2) * h->emit_chunks.size()));
+  L.ltiles = ar.take(std::max<size_t>(256, sizeof(int4) * h->leaf_tiles.size()));
   L.total = ar.off;
   *workspace_bytes = L.total;
   h->planned = true;
@@ -738,6 +737,9 @@ int mra_upload_data(mra_handle* h, const double* locs, const double* obs, void* 
                        cudaMemcpyHostToDevice, st));
   if (!h->gather_rows.empty())
     CU(cudaMemcpyAsync(h->ws + L.gather, h->gather_rows.data(), sizeof(int) * h->gather_rows.size(),
+                       cudaMemcpyHostToDevice, st));
+  if (!h->leaf_tiles.empty())
+    CU(cudaMemcpyAsync(h->ws + L.ltiles, h->leaf_tiles.data(), sizeof(int4) * h->leaf_tiles.size(),
                        cudaMemcpyHostToDevice, st));
   if (!h->emit_chunks.empty())
     CU(cudaMemcpyAsync(h->ws + L.chunks, h->emit_chunks.data(), sizeof(int2) * h->emit_chunks.size(),

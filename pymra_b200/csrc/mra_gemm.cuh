@@ -25,11 +25,14 @@ constexpr int NT = 128;       // threads per CTA
 constexpr int NSTAGE = 3;     // cp.async pipeline depth
 constexpr int LDB = TB + 4;   // smem row stride of a resident 64x64 block (== 4 mod 16 doubles)
 
+constexpr int MAXSEG = 8;     // K segments per tile_gemm_seg call
+
 struct GemmSmem {
   double a[NSTAGE][TB * KC];
   double b[NSTAGE][TB * KC];
-  const double* row_a[TB];
-  const double* row_b[TB];
+  const double* row_a[MAXSEG][TB];
+  const double* row_b[MAXSEG][TB];
+  int seg_k[MAXSEG];
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -135,12 +138,12 @@ __device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSme
   __syncthreads();   // previous users of the stages / row tables (and of resident operands) are done
   if (A_GLOBAL) {
     if (threadIdx.x < TB) {
-      if constexpr (A_GLOBAL) sm.row_a[threadIdx.x] = fa((int)threadIdx.x);
+      if constexpr (A_GLOBAL) sm.row_a[0][threadIdx.x] = fa((int)threadIdx.x);
     }
   }
   if (B_GLOBAL) {
     if (threadIdx.x >= NT - TB) {
-      if constexpr (B_GLOBAL) sm.row_b[threadIdx.x - (NT - TB)] = fb((int)threadIdx.x - (NT - TB));
+      if constexpr (B_GLOBAL) sm.row_b[0][threadIdx.x - (NT - TB)] = fb((int)threadIdx.x - (NT - TB));
     }
   }
   __syncthreads();
@@ -148,8 +151,8 @@ __device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSme
 #pragma unroll
   for (int s = 0; s < NSTAGE - 1; ++s) {
     if (s < nk) {
-      if (A_GLOBAL) stage_load<VEC>(sm.a[s], sm.row_a, s * KC, K, dummy);
-      if (B_GLOBAL) stage_load<VEC>(sm.b[s], sm.row_b, s * KC, K, dummy);
+      if (A_GLOBAL) stage_load<VEC>(sm.a[s], sm.row_a[0], s * KC, K, dummy);
+      if (B_GLOBAL) stage_load<VEC>(sm.b[s], sm.row_b[0], s * KC, K, dummy);
     }
     cp_async_commit();
   }
@@ -162,8 +165,8 @@ __device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSme
       int nb = buf + NSTAGE - 1;
       if (nb >= NSTAGE) nb -= NSTAGE;
       if (kn < nk) {
-        if (A_GLOBAL) stage_load<VEC>(sm.a[nb], sm.row_a, kn * KC, K, dummy);
-        if (B_GLOBAL) stage_load<VEC>(sm.b[nb], sm.row_b, kn * KC, K, dummy);
+        if (A_GLOBAL) stage_load<VEC>(sm.a[nb], sm.row_a[0], kn * KC, K, dummy);
+        if (B_GLOBAL) stage_load<VEC>(sm.b[nb], sm.row_b[0], kn * KC, K, dummy);
       }
       cp_async_commit();
     }
@@ -179,6 +182,59 @@ __device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSme
       else return fb(row, k0 + kk);
     };
     chunk_mma(acc, ga, gb);
+    if (++buf == NSTAGE) buf = 0;
+  }
+  cp_async_wait<0>();
+}
+
+// acc += sum_s A_s B_s^T over up to MAXSEG K-segments, all operands in global memory, as ONE pipelined
+// stream of chunks (no pipeline drain between segments).  fa(s, rr) / fb(s, rr) -> row pointer of tile row
+// rr in segment s (nullptr = zero row), fk(s) -> K of segment s (may be 0).
+template <int VEC, class FA, class FB, class FK>
+__device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, FK fk, GemmSmem& sm,
+                                              const double* dummy) {
+  __syncthreads();
+  for (int s = 0; s < nseg; ++s) {
+    if (threadIdx.x < TB) sm.row_a[s][threadIdx.x] = fa(s, (int)threadIdx.x);
+    else sm.row_b[s][threadIdx.x - TB] = fb(s, (int)threadIdx.x - TB);
+    if (threadIdx.x == 0) sm.seg_k[s] = fk(s);
+  }
+  __syncthreads();
+  int nk = 0;
+  for (int s = 0; s < nseg; ++s) nk += (sm.seg_k[s] + KC - 1) / KC;
+  // loader cursor
+  int lseg = 0, lk0 = 0;
+  auto load_next = [&](int buf) {
+    while (lseg < nseg && lk0 >= sm.seg_k[lseg]) {
+      ++lseg;
+      lk0 = 0;
+    }
+    if (lseg < nseg) {
+      const int K = sm.seg_k[lseg];
+      stage_load<VEC>(sm.a[buf], sm.row_a[lseg], lk0, K, dummy);
+      stage_load<VEC>(sm.b[buf], sm.row_b[lseg], lk0, K, dummy);
+      lk0 += KC;
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) {
+    if (s < nk) load_next(s);
+    cp_async_commit();
+  }
+  int buf = 0;
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();
+    {
+      int nb = buf + NSTAGE - 1;
+      if (nb >= NSTAGE) nb -= NSTAGE;
+      if (kt + NSTAGE - 1 < nk) load_next(nb);
+      cp_async_commit();
+    }
+    const double* sa = sm.a[buf];
+    const double* sb = sm.b[buf];
+    chunk_mma(acc, [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; },
+              [&](int row, int kk) -> double { return sb[stage_pos(row, kk)]; });
     if (++buf == NSTAGE) buf = 0;
   }
   cp_async_wait<0>();

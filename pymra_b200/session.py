@@ -2,6 +2,7 @@
 structure and one data set.  MRATree uses it for the reference-shaped API; bench.py uses it
 directly to time device-resident passes.  PyTorch supplies the arena and the stream only."""
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -31,10 +32,13 @@ class DeviceSession(object):
         self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.lib = _ffi.lib()
         self.h = C.c_void_p()
+        self.timings = {}
+        t0 = time.perf_counter()
         st = self.lib.mra_create(C.byref(self.h), self.dev.index)
         if st != 0:
             raise _ffi.MraError(st, "mra_create failed (no usable CUDA device?)")
         self._set_structure()
+        self.timings["set_structure"] = time.perf_counter() - t0
         self.group, self.world, self.rank, self.shard_level, self.summary = None, 1, 0, 0, None
         if group is not None or emulate is not None:
             from .shard import plan_shards
@@ -52,15 +56,19 @@ class DeviceSession(object):
                 self.check(self.lib.mra_summary_size(self.h, C.byref(n)))
                 self.summary = torch.zeros(int(n.value), dtype=torch.float64, device=self.dev)
                 self.shard_level = s
+        t0 = time.perf_counter()
         obs_c = np.ascontiguousarray(np.asarray(obs, dtype=np.float64).reshape(self.N))
         locs_c = np.ascontiguousarray(np.asarray(locs, dtype=np.float64).reshape(self.N, structure.d))
         nbytes = C.c_size_t()
         self.check(self.lib.mra_plan(self.h, _dptr(obs_c), 1 if want_predict else 0, C.byref(nbytes)))
+        t1 = time.perf_counter()
         self.workspace_bytes = int(nbytes.value)
         self.ws = torch.empty(self.workspace_bytes + 256, dtype=torch.uint8, device=self.dev)
         aligned = (self.ws.data_ptr() + 255) // 256 * 256
         self.check(self.lib.mra_bind_workspace(self.h, C.c_void_p(aligned), C.c_size_t(self.workspace_bytes)))
+        t2 = time.perf_counter()
         self.upload(locs_c, obs_c)
+        self.timings.update(plan=t1 - t0, alloc_bind=t2 - t1, upload=time.perf_counter() - t2)
 
     # ---- plumbing
     def check(self, status):
