@@ -141,16 +141,16 @@ DevCtx make_ctx(mra_handle* h) {
 }
 
 constexpr size_t GS = sizeof(GemmSmem);
-size_t smem_knot(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + 3 * r) + sizeof(int) * r + 16; }
+size_t smem_knot(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + 3 * r + NT * 9) + sizeof(int) * r + 16; }
 size_t smem_prior(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;
   return GS + sizeof(double) * ((size_t)TB * ldT + 2 * r + 2 * TB) + sizeof(int) * TB;
 }
 size_t smem_gram() { return GS + sizeof(int) * 2 * TB; }
-size_t smem_chol() { return GS + sizeof(double) * ((size_t)2 * TB * LDB + TB); }
+size_t smem_chol() { return GS + sizeof(double) * ((size_t)TB * LDB + TB + NT * 9); }
 size_t smem_solve() { return GS + sizeof(double) * ((size_t)TB * LDB); }
 size_t smem_plain() { return GS; }
-size_t smem_factor(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + r); }
+size_t smem_factor(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + r + NT * 9); }
 size_t smem_predict(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;
   return GS + sizeof(double) * ((size_t)TB * ldT + 2 * TB) + sizeof(int) * MAX_LEVELS;
@@ -177,7 +177,7 @@ cudaError_t configure_vec(int r) {
   SET_(k_knot_factor<V_>, smem_knot(r));
   SET_(k_prior_tiles<V_>, smem_prior(r));
   SET_(k_leaf_gram<V_>, smem_gram());
-  SET_(k_leaf_chol_step<V_>, smem_chol());
+  SET_(k_leaf_factor<V_>, smem_chol());
   SET_(k_leaf_solve<V_>, smem_solve());
   SET_(k_assemble_A<V_>, smem_plain());
   SET_(k_node_factor<V_>, smem_factor(r));
@@ -295,10 +295,7 @@ int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary)
     const int nbo = (h->max_leaf_obs + TB - 1) / TB;
     dim3 g1(nleaf, nbo * (nbo + 1) / 2);
     MRA_FOR_VEC(h, LAUNCH("leaf_gram", k_leaf_gram<V_><<<g1, NT, smem_gram(), st>>>(c, leaf_list, 0)));
-    for (int p = 0; p < nbo; ++p) {
-      dim3 g2(nleaf, nbo - p);
-      MRA_FOR_VEC(h, LAUNCH("leaf_chol", k_leaf_chol_step<V_><<<g2, NT, smem_chol(), st>>>(c, leaf_list, p)));
-    }
+    MRA_FOR_VEC(h, LAUNCH("leaf_chol", k_leaf_factor<V_><<<nleaf, NT, smem_chol(), st>>>(c, leaf_list)));
     dim3 g3(nleaf, (h->max_leaf_W + TB - 1) / TB);
     MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve<V_><<<g3, NT, smem_solve(), st>>>(c, leaf_list, 0)));
   }
