@@ -15,6 +15,7 @@ the full likelihood and predictions.
 """
 import logging
 import time
+import weakref
 
 import numpy as np
 
@@ -52,7 +53,7 @@ class _Root(object):
     """The attributes of the reference's root Node that callers touch."""
 
     def __init__(self, tree):
-        self._tree = tree
+        self._tree_ref = weakref.ref(tree)     # no reference cycle: the device arena is released with the tree
         self.children = []
         self.ID = "r"
         self.res = 0
@@ -61,6 +62,13 @@ class _Root(object):
         self.kInds = tree._structure.node_kinds_local[0]
         self.d = tree._d
         self.u = np.matrix([[tree._u]])
+
+    @property
+    def _tree(self):
+        t = self._tree_ref()
+        if t is None:
+            raise ReferenceError("the MRATree this root belonged to has been deleted")
+        return t
 
     @property
     def mean(self):

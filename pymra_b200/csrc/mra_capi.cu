@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mra_kernels.cuh"
@@ -91,6 +92,23 @@ struct mra_handle {
 
 namespace {
 
+// Splits [0, n) over a few host threads (the host-side O(N) passes of plan / set_structure).
+template <class F>
+void parallel_for(int64_t n, F fn) {
+  unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  if (n < (int64_t)1 << 18 || nt == 1) {
+    fn((int64_t)0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int64_t step = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; ++t) {
+    const int64_t a = (int64_t)t * step, b = std::min(n, a + step);
+    if (a < b) th.emplace_back([=] { fn(a, b); });
+  }
+  for (auto& t : th) t.join();
+}
+
 int fail(mra_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
@@ -144,16 +162,16 @@ constexpr size_t GS = sizeof(GemmSmem);
 size_t smem_knot(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + 3 * r + NT * 9) + sizeof(int) * r + 16; }
 size_t smem_prior(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;
-  return GS + sizeof(double) * ((size_t)TB * ldT + 2 * r + 2 * TB) + sizeof(int) * TB;
+  return GS + sizeof(double) * ((size_t)(r > TB ? TB * ldT : 0) + 2 * r + 2 * TB) + sizeof(int) * TB;
 }
 size_t smem_gram() { return GS + sizeof(int) * 2 * TB; }
 size_t smem_chol() { return GS + sizeof(double) * ((size_t)TB * LDB + TB + NT * 9); }
-size_t smem_solve() { return GS + sizeof(double) * ((size_t)TB * LDB); }
+size_t smem_solve() { return GS; }
 size_t smem_plain() { return GS; }
 size_t smem_factor(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + r + NT * 9); }
 size_t smem_predict(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;
-  return GS + sizeof(double) * ((size_t)TB * ldT + 2 * TB) + sizeof(int) * MAX_LEVELS;
+  return GS + sizeof(double) * ((size_t)(r > TB ? TB * ldT : 0) + 2 * TB) + sizeof(int) * MAX_LEVELS;
 }
 
 // Kernels are instantiated for VEC = 2 (16-byte cp.async, even r) and VEC = 1 (odd r).
@@ -514,9 +532,19 @@ int mra_set_structure(mra_handle* h, const mra_structure* s) {
     h->knot_rows[i] = (int)s->knot_rows[i];
   }
   h->perm.resize(h->N);
-  for (int64_t i = 0; i < h->N; ++i) {
-    if (s->perm[i] < 0 || s->perm[i] >= h->N) return fail(h, MRA_ERR_ARG, "perm entry out of range");
-    h->perm[i] = (int)s->perm[i];
+  {
+    std::vector<int> bad(1, 0);
+    int* badp = bad.data();
+    int* dst = h->perm.data();
+    const int64_t* src = s->perm;
+    const int64_t N = h->N;
+    parallel_for(N, [=](int64_t a, int64_t b) {
+      for (int64_t i = a; i < b; ++i) {
+        if (src[i] < 0 || src[i] >= N) *badp = 1;
+        dst[i] = (int)src[i];
+      }
+    });
+    if (bad[0]) return fail(h, MRA_ERR_ARG, "perm entry out of range");
   }
   for (int n = 0; n < nn; ++n) {
     const int lv = h->level[n];
@@ -552,6 +580,14 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   h->max_leaf_W = 1;
   for (auto& f : h->kflops) f = 0.0;
   for (auto& f : h->kbytes) f = 0.0;
+  std::vector<uint8_t> finite_row((size_t)h->N);     // np.isfinite(obs) in tree order (MRANode.py:415)
+  {
+    uint8_t* fr = finite_row.data();
+    const int* pm = h->perm.data();
+    parallel_for(h->N, [=](int64_t a, int64_t b) {
+      for (int64_t i = a; i < b; ++i) fr[i] = std::isfinite(obs[pm[i]]) ? 1 : 0;
+    });
+  }
   for (int n = 0; n < nn; ++n) {
     NodeDev& d = h->nodes[n];
     d.level = h->level[n];
@@ -593,7 +629,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       if (d.kind == KIND_LEAF) {
         for (int64_t i = 0; i < h->row_count[n]; ++i) {
           const int64_t row = h->row_start[n] + i;
-          if (std::isfinite(obs[h->perm[row]])) h->obs_rows.push_back((int)row);
+          if (finite_row[row]) h->obs_rows.push_back((int)row);
         }
       }
       d.n_obs = (int)h->obs_rows.size() - d.obs_off;

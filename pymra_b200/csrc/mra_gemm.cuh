@@ -1,13 +1,16 @@
 // FP64 tile GEMM core of the MRA kernels (sm_100a).
 //
-// One primitive: a 64x64 accumulator tile per 128-thread CTA (4 warps, 2x2 of 32x32),
+// One primitive: a 64x64 accumulator tile per 128-thread CTA (4 warps, each owning 16 full rows),
 //     acc += A(64 x K) * B(64 x K)^T,   both operands K-contiguous ("NT"),
 // computed with FP64 tensor-core MMA (mma.sync m8n8k4 -> SASS DMMA.8x8x4, the only FP64 MMA
 // shape sm_100a has).  Operands living in global memory are streamed through a 3-stage
 // cp.async (LDGSTS) pipeline of 64 x 16 chunks; the chunks are stored with an XOR swizzle of
 // their 16-byte columns so the 8x4 fragment loads are bank-conflict free without padding.
-// Operands that already live in shared memory (the T / D / P tiles of the callers) are read in
-// place through an element functor.
+// Operands that already live in shared memory (the D / P tiles of the callers) are read in
+// place through an element functor.  Because a warp owns complete rows, an accumulator tile can be fed
+// straight back as the A operand of the next product (tile_gemm_regA: quad shuffles turn the C fragment
+// layout into the A fragment layout), so GEMM -> transform -> GEMM chains never touch shared memory and
+// row-wise reductions stay inside a quad.
 //
 // Row sources are described by a functor rr -> const double* (start of the K range of tile row
 // rr, or nullptr for a zero row).  VEC = 2 uses 16-byte copies and needs every row start 16-byte
@@ -41,19 +44,20 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
+// Element (i, j, e) of a thread: tile row 16*warp + 8*i + (lane >> 2), column 8*j + 2*(lane & 3) + e.
 struct Acc {
-  double v[4][4][2];
+  double v[2][8][2];
   __device__ __forceinline__ void zero() {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j][0] = v[i][j][1] = 0.0;
+      for (int j = 0; j < 8; ++j) v[i][j][0] = v[i][j][1] = 0.0;
   }
   __device__ __forceinline__ void negate() {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         v[i][j][0] = -v[i][j][0];
         v[i][j][1] = -v[i][j][1];
       }
@@ -112,20 +116,19 @@ __device__ __forceinline__ void stage_load(double* st, const double* const* rows
 template <class GA, class GB>
 __device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int wm = warp * 16;
   const int g = lane >> 2, q = lane & 3;
 #pragma unroll
   for (int ks = 0; ks < KC; ks += 4) {
-    double a[4], b[4];
+    double a[2], b[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      a[i] = ga(wm + i * 8 + g, ks + q);
-      b[i] = gb(wn + i * 8 + g, ks + q);
-    }
+    for (int i = 0; i < 2; ++i) a[i] = ga(wm + i * 8 + g, ks + q);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 8; ++j) b[j] = gb(j * 8 + g, ks + q);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dmma884(acc.v[i][j], a[i], b[j]);
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dmma884(acc.v[i][j], a[i], b[j]);
   }
 }
 
@@ -240,18 +243,92 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
   cp_async_wait<0>();
 }
 
+// out += Areg * B^T where Areg is a 64 x 64 tile held in accumulator layout (columns >= K must be zero
+// or K a multiple of 4 covering them) and K <= 64.  B_GLOBAL: fb(rr) -> row pointer, streamed through the
+// cp.async stages; else fb(rr, k) -> element of a shared-memory resident operand.
+template <int VEC, bool B_GLOBAL, class FB>
+__device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB fb, GemmSmem& sm,
+                                               const double* dummy) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  __syncthreads();
+  if (B_GLOBAL) {
+    if (threadIdx.x < TB) {
+      if constexpr (B_GLOBAL) sm.row_b[0][threadIdx.x] = fb((int)threadIdx.x);
+    }
+    __syncthreads();
+  }
+  const int nk = (K + KC - 1) / KC;      // <= 4
+  if (B_GLOBAL) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+      if (s < nk) stage_load<VEC>(sm.b[s], sm.row_b[0], s * KC, K, dummy);
+      cp_async_commit();
+    }
+  }
+#pragma unroll
+  for (int kt = 0; kt < TB / KC; ++kt) {
+    if (kt < nk) {
+      const int buf = kt % NSTAGE;
+      if (B_GLOBAL) {
+        cp_async_wait<NSTAGE - 2>();
+        __syncthreads();
+        if (kt + NSTAGE - 1 < nk) stage_load<VEC>(sm.b[(kt + NSTAGE - 1) % NSTAGE], sm.row_b[0], (kt + NSTAGE - 1) * KC, K, dummy);
+        cp_async_commit();
+      }
+      const double* sb = sm.b[buf];
+#pragma unroll
+      for (int ks = 0; ks < KC; ks += 4) {
+        const int st = (kt * KC + ks) >> 2;            // k-step index 0..15 -> source tile st>>1, half st&1
+        const int src = (lane & ~3) | (((st & 1) << 1) | (q >> 1));
+        double a[2], b[8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double v0 = __shfl_sync(0xffffffffu, A.v[i][st >> 1][0], src);
+          const double v1 = __shfl_sync(0xffffffffu, A.v[i][st >> 1][1], src);
+          a[i] = (q & 1) ? v1 : v0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if constexpr (B_GLOBAL) b[j] = sb[stage_pos(j * 8 + g, ks + q)];
+          else b[j] = fb(j * 8 + g, kt * KC + ks + q);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dmma884(out.v[i][j], a[i], b[j]);
+      }
+    }
+  }
+  if (B_GLOBAL) cp_async_wait<0>();
+}
+
+// acc.v = f(row, col, acc.v) element-wise (transform in registers).
+template <class F>
+__device__ __forceinline__ void tile_transform(Acc& acc, F f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp * 16;
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) acc.v[i][j][e] = f(wm + i * 8 + g, j * 8 + q * 2 + e, acc.v[i][j][e]);
+}
+
 // f(row, col, value) for every accumulator element owned by this thread.
 template <class F>
 __device__ __forceinline__ void tile_epilogue(const Acc& acc, F f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int wm = warp * 16;
   const int g = lane >> 2, q = lane & 3;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) f(wm + i * 8 + g, wn + j * 8 + q * 2 + e, acc.v[i][j][e]);
+      for (int e = 0; e < 2; ++e) f(wm + i * 8 + g, j * 8 + q * 2 + e, acc.v[i][j][e]);
 }
 
 }  // namespace mra

@@ -145,10 +145,13 @@ class DeviceSession(object):
             host = out.cpu().numpy()
             self.fetch_likelihood()                           # surfaces a non-SPD status like the plain path
             return host[0].copy(), host[1].copy()
-        mean = np.empty(self.N)
-        sd = np.empty(self.N)
-        self.check(self.lib.mra_run_predict(self.h, self.stream(), _dptr(mean), _dptr(sd)))
-        return mean, sd
+        # page-locked staging (torch's caching host allocator): the device->host copy runs at PCIe rate and the
+        # returned arrays are zero-copy views of it
+        import torch
+        out = torch.empty(2, self.N, dtype=torch.float64, pin_memory=True)
+        host = out.numpy()
+        self.check(self.lib.mra_run_predict(self.h, self.stream(), _dptr(host[0]), _dptr(host[1])))
+        return host[0], host[1]
 
     def predict_dev(self, mean_t=None, sd_t=None, reduce=False):
         """Results into device tensors (caller's order).  Sharded: each rank fills its own rows and zeros
