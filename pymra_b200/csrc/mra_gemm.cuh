@@ -113,10 +113,14 @@ __device__ __forceinline__ void stage_load(double* st, const double* const* rows
 
 // 64 x 64 x 16 of DMMA on one chunk.  ga(row, kk) / gb(row, kk): operand element at tile row `row`,
 // k index kk (0..15) inside the chunk.
+// mrows / ncols: valid extent of the output tile; warps whose 16 rows lie outside and 8-column groups
+// outside are skipped (their accumulators keep their value, zero if the tile was zeroed).
 template <class GA, class GB>
-__device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb) {
+__device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb, int mrows = TB, int ncols = TB) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp * 16;
+  if (wm >= mrows) return;
+  const int nj = (ncols + 7) >> 3;
   const int g = lane >> 2, q = lane & 3;
 #pragma unroll
   for (int ks = 0; ks < KC; ks += 4) {
@@ -124,11 +128,13 @@ __device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) a[i] = ga(wm + i * 8 + g, ks + q);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = gb(j * 8 + g, ks + q);
+    for (int j = 0; j < 8; ++j)
+      if (j < nj) b[j] = gb(j * 8 + g, ks + q);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dmma884(acc.v[i][j], a[i], b[j]);
+      for (int j = 0; j < 8; ++j)
+        if (j < nj) dmma884(acc.v[i][j], a[i], b[j]);
   }
 }
 
@@ -137,7 +143,8 @@ __device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb) {
 //   (shared-memory resident operand; must return 0 for k >= K).  Same for B.
 // Must be called by all 128 threads; safe to call back to back (leading barrier).
 template <int VEC, bool A_GLOBAL, bool B_GLOBAL, class FA, class FB>
-__device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSmem& sm, const double* dummy) {
+__device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSmem& sm, const double* dummy,
+                                          int mrows = TB, int ncols = TB) {
   __syncthreads();   // previous users of the stages / row tables (and of resident operands) are done
   if (A_GLOBAL) {
     if (threadIdx.x < TB) {
@@ -184,7 +191,7 @@ __device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSme
       if constexpr (B_GLOBAL) return sb[stage_pos(row, kk)];
       else return fb(row, k0 + kk);
     };
-    chunk_mma(acc, ga, gb);
+    chunk_mma(acc, ga, gb, mrows, ncols);
     if (++buf == NSTAGE) buf = 0;
   }
   cp_async_wait<0>();
@@ -195,7 +202,7 @@ __device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSme
 // rr in segment s (nullptr = zero row), fk(s) -> K of segment s (may be 0).
 template <int VEC, class FA, class FB, class FK>
 __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, FK fk, GemmSmem& sm,
-                                              const double* dummy) {
+                                              const double* dummy, int mrows = TB, int ncols = TB) {
   __syncthreads();
   for (int s = 0; s < nseg; ++s) {
     if (threadIdx.x < TB) sm.row_a[s][threadIdx.x] = fa(s, (int)threadIdx.x);
@@ -237,7 +244,7 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
     const double* sa = sm.a[buf];
     const double* sb = sm.b[buf];
     chunk_mma(acc, [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; },
-              [&](int row, int kk) -> double { return sb[stage_pos(row, kk)]; });
+              [&](int row, int kk) -> double { return sb[stage_pos(row, kk)]; }, mrows, ncols);
     if (++buf == NSTAGE) buf = 0;
   }
   cp_async_wait<0>();
@@ -248,9 +255,11 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
 // cp.async stages; else fb(rr, k) -> element of a shared-memory resident operand.
 template <int VEC, bool B_GLOBAL, class FB>
 __device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB fb, GemmSmem& sm,
-                                               const double* dummy) {
+                                               const double* dummy, int mrows = TB, int ncols = TB) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
+  const bool active = (int)(threadIdx.x >> 5) * 16 < mrows;
+  const int nj = (ncols + 7) >> 3;
   __syncthreads();
   if (B_GLOBAL) {
     if (threadIdx.x < TB) {
@@ -277,6 +286,7 @@ __device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB
         cp_async_commit();
       }
       const double* sb = sm.b[buf];
+      if (active)
 #pragma unroll
       for (int ks = 0; ks < KC; ks += 4) {
         const int st = (kt * KC + ks) >> 2;            // k-step index 0..15 -> source tile st>>1, half st&1
@@ -290,13 +300,16 @@ __device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if constexpr (B_GLOBAL) b[j] = sb[stage_pos(j * 8 + g, ks + q)];
-          else b[j] = fb(j * 8 + g, kt * KC + ks + q);
+          if (j < nj) {
+            if constexpr (B_GLOBAL) b[j] = sb[stage_pos(j * 8 + g, ks + q)];
+            else b[j] = fb(j * 8 + g, kt * KC + ks + q);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dmma884(out.v[i][j], a[i], b[j]);
+          for (int j = 0; j < 8; ++j)
+            if (j < nj) dmma884(out.v[i][j], a[i], b[j]);
       }
     }
   }
