@@ -113,14 +113,14 @@ __device__ __forceinline__ void stage_load(double* st, const double* const* rows
 
 // 64 x 64 x 16 of DMMA on one chunk.  ga(row, kk) / gb(row, kk): operand element at tile row `row`,
 // k index kk (0..15) inside the chunk.
-// mrows / ncols: valid extent of the output tile; warps whose 16 rows lie outside and 8-column groups
-// outside are skipped (their accumulators keep their value, zero if the tile was zeroed).
+// mrows: valid rows of the output tile; warps whose 16 rows lie outside are skipped (their accumulators
+// keep their value, zero if the tile was zeroed).  Column-group predication was measured slower (r01g).
 template <class GA, class GB>
 __device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb, int mrows = TB, int ncols = TB) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp * 16;
   if (wm >= mrows) return;
-  const int nj = (ncols + 7) >> 3;
+  (void)ncols;
   const int g = lane >> 2, q = lane & 3;
 #pragma unroll
   for (int ks = 0; ks < KC; ks += 4) {
@@ -128,13 +128,11 @@ __device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb, int mrows = TB
 #pragma unroll
     for (int i = 0; i < 2; ++i) a[i] = ga(wm + i * 8 + g, ks + q);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nj) b[j] = gb(j * 8 + g, ks + q);
+    for (int j = 0; j < 8; ++j) b[j] = gb(j * 8 + g, ks + q);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nj) dmma884(acc.v[i][j], a[i], b[j]);
+      for (int j = 0; j < 8; ++j) dmma884(acc.v[i][j], a[i], b[j]);
   }
 }
 
@@ -259,7 +257,7 @@ __device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const bool active = (int)(threadIdx.x >> 5) * 16 < mrows;
-  const int nj = (ncols + 7) >> 3;
+  (void)ncols;
   __syncthreads();
   if (B_GLOBAL) {
     if (threadIdx.x < TB) {
@@ -300,16 +298,13 @@ __device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (j < nj) {
-            if constexpr (B_GLOBAL) b[j] = sb[stage_pos(j * 8 + g, ks + q)];
-            else b[j] = fb(j * 8 + g, kt * KC + ks + q);
-          }
+          if constexpr (B_GLOBAL) b[j] = sb[stage_pos(j * 8 + g, ks + q)];
+          else b[j] = fb(j * 8 + g, kt * KC + ks + q);
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < nj) dmma884(out.v[i][j], a[i], b[j]);
+          for (int j = 0; j < 8; ++j) dmma884(out.v[i][j], a[i], b[j]);
       }
     }
   }
