@@ -14,6 +14,9 @@
 #include "../../include/pymra_b200.h"
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
+#include <thread>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -329,6 +332,318 @@ struct Builder {
   }
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Two-phase build for regular trees (every node above level M has > 100 rows and four non-empty
+// quadrants).  The quadrant partition of the locations does not depend on the RNG, so worker threads
+// compute it level by level (BFS) and publish, per level, the quadrant code of every position as two
+// bit planes with cumulative block counts.  The calling thread replays the reference's DFS / legacy RNG
+// stream on top of that with O(1) rank queries: child ranges, the quadrant of every knot and its position
+// inside the child all come from the bit planes, so it never touches the 20 bytes/location row data.
+struct LevelBits {
+  std::vector<uint64_t> lo, hi;    // code = 2*[x > mean_x] + [y > mean_y]: hi = x bit, lo = y bit
+  std::vector<int32_t> cum;        // cum[4*b + c] = #positions < 64*b with code c (whole level)
+  inline int code(int64_t x) const {
+    const int64_t b = x >> 6;
+    const int sh = (int)(x & 63);
+    return (int)(((hi[b] >> sh) & 1ull) * 2 + ((lo[b] >> sh) & 1ull));
+  }
+  inline int64_t rank(int c, int64_t x) const {      // #positions < x with code c
+    const int64_t b = x >> 6;
+    const uint64_t wl = (c & 1) ? lo[b] : ~lo[b], wh = (c & 2) ? hi[b] : ~hi[b];
+    const uint64_t low = (x & 63) ? ((1ull << (x & 63)) - 1ull) : 0ull;
+    return (int64_t)cum[4 * b + c] + __builtin_popcountll(wl & wh & low);
+  }
+};
+
+template <class F>
+void run_parallel(int nthreads, int64_t nitems, F fn) {    // fn(item) for item in [0, nitems)
+  if (nitems <= 0) return;
+  const int nt = (int)std::min<int64_t>(nthreads, nitems);
+  if (nt <= 1) {
+    for (int64_t i = 0; i < nitems; ++i) fn(i);
+    return;
+  }
+  std::atomic<int64_t> next{0};
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&] {
+      for (int64_t i; (i = next.fetch_add(1)) < nitems;) fn(i);
+    });
+  for (auto& t : th) t.join();
+}
+
+struct Partitioner {
+  int64_t N = 0;
+  int M = 0, nthreads = 1;
+  int32_t* rows[2];
+  double *xs[2], *ys[2];
+  uint8_t* code = nullptr;
+  std::vector<LevelBits> lv;
+  std::atomic<int> ready{0};
+  std::atomic<int> failed{0};
+  struct PNode {
+    int64_t s, e;
+    double sx, sy;
+  };
+  static constexpr int64_t BIG = 1 << 18;
+
+  // codes and counts of positions [a, b) of a node with means (mx, my)
+  static void pass1(const double* X, const double* Y, uint8_t* C, int64_t a, int64_t b, double mx, double my,
+                    int64_t cnt[4]) {
+    int64_t nx = 0, ny = 0, nxy = 0;
+    for (int64_t i = a; i < b; ++i) {
+      const int gx = X[i] > mx, gy = Y[i] > my;
+      C[i] = (uint8_t)(2 * gx + gy);
+      nx += gx;
+      ny += gy;
+      nxy += gx & gy;
+    }
+    cnt[0] = (b - a) - nx - ny + nxy;
+    cnt[1] = ny - nxy;
+    cnt[2] = nx - nxy;
+    cnt[3] = nxy;
+  }
+
+  void do_node(const PNode& nd, PNode* ch, int b) {
+    const int64_t n = nd.e - nd.s;
+    if (n <= 100) {
+      failed.store(1);
+      return;
+    }
+    const double mx = nd.sx / (double)n, my = nd.sy / (double)n;
+    const int32_t* R = rows[b];
+    const double *X = xs[b], *Y = ys[b];
+    int32_t* R2 = rows[b ^ 1];
+    double *X2 = xs[b ^ 1], *Y2 = ys[b ^ 1];
+    int64_t cnt[4], off[4];
+    if (n < BIG) {
+      pass1(X, Y, code, nd.s, nd.e, mx, my, cnt);
+      off[0] = nd.s;
+      for (int c = 1; c < 4; ++c) off[c] = off[c - 1] + cnt[c - 1];
+      int64_t w[4] = {off[0], off[1], off[2], off[3]};
+      double csx[4] = {0, 0, 0, 0}, csy[4] = {0, 0, 0, 0};
+      for (int64_t i = nd.s; i < nd.e; ++i) {
+        const int c = code[i];
+        const int64_t d = w[c]++;
+        R2[d] = R[i];
+        const double x = X[i], y = Y[i];
+        X2[d] = x;
+        Y2[d] = y;
+        csx[c] += x;
+        csy[c] += y;
+      }
+      for (int c = 0; c < 4; ++c) ch[c] = PNode{off[c], off[c] + cnt[c], csx[c], csy[c]};
+    } else {
+      // cooperative path: all threads on one node (chunked codes, chunked stable scatter, then the
+      // children's sums one thread each, in row order as np.mean needs)
+      const int nc = nthreads * 4;
+      const int64_t step = (n + nc - 1) / nc;
+      std::vector<int64_t> cc((size_t)nc * 4, 0);
+      run_parallel(nthreads, nc, [&](int64_t k) {
+        const int64_t a = nd.s + k * step, bb = std::min(nd.e, a + step);
+        if (a < bb) pass1(X, Y, code, a, bb, mx, my, &cc[4 * k]);
+      });
+      for (int c = 0; c < 4; ++c) {
+        cnt[c] = 0;
+        for (int k = 0; k < nc; ++k) cnt[c] += cc[4 * k + c];
+      }
+      off[0] = nd.s;
+      for (int c = 1; c < 4; ++c) off[c] = off[c - 1] + cnt[c - 1];
+      std::vector<int64_t> w0((size_t)nc * 4);
+      for (int c = 0; c < 4; ++c) {
+        int64_t acc = off[c];
+        for (int k = 0; k < nc; ++k) {
+          w0[4 * k + c] = acc;
+          acc += cc[4 * k + c];
+        }
+      }
+      run_parallel(nthreads, nc, [&](int64_t k) {
+        const int64_t a = nd.s + k * step, bb = std::min(nd.e, a + step);
+        int64_t w[4] = {w0[4 * k], w0[4 * k + 1], w0[4 * k + 2], w0[4 * k + 3]};
+        for (int64_t i = a; i < bb; ++i) {
+          const int64_t d = w[code[i]]++;
+          R2[d] = R[i];
+          X2[d] = X[i];
+          Y2[d] = Y[i];
+        }
+      });
+      run_parallel(nthreads, 4, [&](int64_t c) {
+        double sx = 0.0, sy = 0.0;
+        for (int64_t i = off[c]; i < off[c] + cnt[c]; ++i) {
+          sx += X2[i];
+          sy += Y2[i];
+        }
+        ch[c] = PNode{off[c], off[c] + cnt[c], sx, sy};
+      });
+    }
+    for (int c = 0; c < 4; ++c)
+      if (cnt[c] == 0) failed.store(1);
+  }
+
+  void build_bits(int L) {
+    LevelBits& lb = lv[L];
+    const int64_t nblk = (N >> 6) + 2;
+    lb.lo.assign(nblk, 0);
+    lb.hi.assign(nblk, 0);
+    lb.cum.assign(nblk * 4, 0);
+    const int nc = nthreads * 2;
+    const int64_t bstep = (nblk + nc - 1) / nc;
+    std::vector<int64_t> cc((size_t)nc * 4, 0);
+    run_parallel(nthreads, nc, [&](int64_t k) {
+      const int64_t b0 = k * bstep, b1 = std::min(nblk, b0 + bstep);
+      int64_t c4[4] = {0, 0, 0, 0};
+      for (int64_t b = b0; b < b1; ++b) {
+        uint64_t wl = 0, wh = 0;
+        const int64_t x0 = b << 6, x1 = std::min(N, x0 + 64);
+        for (int64_t x = x0; x < x1; ++x) {
+          const uint64_t cd = code[x];
+          wl |= (cd & 1ull) << (x - x0);
+          wh |= (cd >> 1) << (x - x0);
+        }
+        lb.lo[b] = wl;
+        lb.hi[b] = wh;
+        const int64_t nvalid = std::max<int64_t>(0, x1 - x0);
+        const uint64_t valid = nvalid >= 64 ? ~0ull : ((1ull << nvalid) - 1ull);
+        lb.cum[4 * b + 0] = (int32_t)__builtin_popcountll(~wl & ~wh & valid);   // per-block counts for now
+        lb.cum[4 * b + 1] = (int32_t)__builtin_popcountll(wl & ~wh & valid);
+        lb.cum[4 * b + 2] = (int32_t)__builtin_popcountll(~wl & wh & valid);
+        lb.cum[4 * b + 3] = (int32_t)__builtin_popcountll(wl & wh & valid);
+        for (int c = 0; c < 4; ++c) c4[c] += lb.cum[4 * b + c];
+      }
+      for (int c = 0; c < 4; ++c) cc[4 * k + c] = c4[c];
+    });
+    std::vector<int64_t> base((size_t)nc * 4, 0);
+    for (int c = 0; c < 4; ++c) {
+      int64_t acc = 0;
+      for (int k = 0; k < nc; ++k) {
+        base[4 * k + c] = acc;
+        acc += cc[4 * k + c];
+      }
+    }
+    run_parallel(nthreads, nc, [&](int64_t k) {
+      const int64_t b0 = k * bstep, b1 = std::min(nblk, b0 + bstep);
+      int64_t run[4] = {base[4 * k], base[4 * k + 1], base[4 * k + 2], base[4 * k + 3]};
+      for (int64_t b = b0; b < b1; ++b)
+        for (int c = 0; c < 4; ++c) {
+          const int32_t own = lb.cum[4 * b + c];
+          lb.cum[4 * b + c] = (int32_t)run[c];
+          run[c] += own;
+        }
+    });
+  }
+
+  void run(double sx0, double sy0) {
+    std::vector<PNode> cur{PNode{0, N, sx0, sy0}}, next;
+    for (int L = 0; L < M; ++L) {
+      next.assign(cur.size() * 4, PNode{0, 0, 0.0, 0.0});
+      const int b = L & 1;
+      // big nodes one after the other (all threads inside), the rest in parallel
+      std::vector<int64_t> small;
+      for (size_t i = 0; i < cur.size(); ++i) {
+        if (cur[i].e - cur[i].s >= BIG) do_node(cur[i], &next[4 * i], b);
+        else small.push_back((int64_t)i);
+      }
+      run_parallel(nthreads, (int64_t)small.size(), [&](int64_t k) {
+        const int64_t i = small[k];
+        do_node(cur[i], &next[4 * i], b);
+      });
+      if (failed.load()) {
+        ready.store(M + 1, std::memory_order_release);
+        return;
+      }
+      build_bits(L);
+      ready.store(L + 1, std::memory_order_release);
+      cur.swap(next);
+    }
+  }
+};
+
+struct RankBuilder {
+  Builder* B;
+  Partitioner* P;
+  int M;
+
+  void visit(int parent, int level, int64_t s, int64_t e, int levels_left, const std::vector<KEnt>& kp) {
+    Builder& b = *B;
+    if (b.status) return;
+    const int me = (int)b.rec.size();
+    b.rec.push_back(Rec{level, parent, MRA_NODE_LEAF, s, e - s, -1, 0, -1});
+    const int64_t n = e - s;
+    const int64_t n_nk = n - (int64_t)kp.size();
+    const bool internal = levels_left > 0 && n_nk > std::max(b.r, b.J);
+    if (!internal) {
+      if (levels_left > 0) {       // ragged tree (early leaf): the serial builder handles it
+        b.status = 1;
+        return;
+      }
+      for (const KEnt& k : kp) b.knot_tree_row[k.id] = (int32_t)(s + k.pos);
+      return;
+    }
+    if (n_nk <= 100 || n <= 100) {
+      b.status = 1;
+      return;
+    }
+    int32_t pick[256];
+    b.first_r_of_permutation(n_nk, pick);
+    std::sort(pick, pick + b.r);
+    b.rec[me].kind = MRA_NODE_INTERNAL;
+    b.rec[me].knot_off = (int64_t)b.kinds_local.size();
+    std::vector<KEnt> mk;
+    mk.reserve(kp.size() + b.r);
+    {
+      size_t j = 0;
+      for (int t = 0; t < b.r; ++t) {
+        int32_t pos = pick[t] + (int32_t)j;
+        while (j < kp.size() && kp[j].pos <= pos) {
+          mk.push_back(kp[j]);
+          ++j;
+          ++pos;
+        }
+        const int32_t id = (int32_t)b.kinds_local.size();
+        b.kinds_local.push_back(pos);
+        b.knot_tree_row.push_back(-1);
+        mk.push_back(KEnt{pos, id});
+      }
+      for (; j < kp.size(); ++j) mk.push_back(kp[j]);
+    }
+    while (P->ready.load(std::memory_order_acquire) <= level) std::this_thread::yield();
+    if (P->failed.load()) {
+      b.status = 1;
+      return;
+    }
+    const LevelBits& lb = P->lv[level];
+    int64_t base[4], cnt[4], off[4];
+    for (int c = 0; c < 4; ++c) {
+      base[c] = lb.rank(c, s);
+      cnt[c] = lb.rank(c, e) - base[c];
+      if (cnt[c] == 0) {
+        b.status = 1;
+        return;
+      }
+    }
+    off[0] = s;
+    for (int c = 1; c < 4; ++c) off[c] = off[c - 1] + cnt[c - 1];
+    std::vector<KEnt> ckp[4];
+    for (const KEnt& k : mk) {
+      const int64_t x = s + k.pos;
+      const int c = lb.code(x);
+      ckp[c].push_back(KEnt{(int32_t)(lb.rank(c, x) - base[c]), k.id});
+    }
+    const bool fork = level == b.critDepth;
+    MT saved;
+    if (fork) saved = b.rng;
+    b.rec[me].n_child = 4;
+    for (int c = 0; c < 4; ++c) {
+      if (fork) b.rng = saved;
+      if (c == 0) b.rec[me].first_child = (int)b.rec.size();
+      visit(me, level + 1, off[c], off[c] + cnt[c], levels_left - 1, ckp[c]);
+      if (b.status) return;
+    }
+    if (fork) b.rng = saved;
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -380,7 +695,44 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
     sx += x;
     sy += y;
   }
-  B.visit(-1, 0, 0, N, 0, M, std::vector<KEnt>(), sx, sy);
+  bool done = false;
+  if (M >= 1 && N >= (int64_t)1 << 16) {
+    // threaded two-phase build; falls back to the serial DFS below when the tree is not regular
+    Partitioner P;
+    P.N = N;
+    P.M = M;
+    P.nthreads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    for (int b = 0; b < 2; ++b) {
+      P.rows[b] = B.rows[b];
+      P.xs[b] = B.xs[b];
+      P.ys[b] = B.ys[b];
+    }
+    P.code = B.code;
+    P.lv.resize(M);
+    std::thread worker([&] { P.run(sx, sy); });
+    RankBuilder RB{&B, &P, M};
+    RB.visit(-1, 0, 0, N, M, std::vector<KEnt>());
+    worker.join();
+    if (!B.status && !P.failed.load()) {
+      std::memcpy(B.perm, B.rows[M & 1], sizeof(int32_t) * N);
+      done = true;
+    } else {
+      // restart serially from the caller's RNG state and the original row order
+      B.status = 0;
+      B.rec.clear();
+      B.kinds_local.clear();
+      B.knot_tree_row.clear();
+      std::memcpy(B.rng.key, mt_key, sizeof(uint32_t) * 624);
+      B.rng.pos = *mt_pos;
+      B.rng.out_valid = false;
+      for (int64_t i = 0; i < N; ++i) {
+        B.rows[0][i] = (int32_t)i;
+        B.xs[0][i] = locs[2 * i];
+        B.ys[0][i] = locs[2 * i + 1];
+      }
+    }
+  }
+  if (!done) B.visit(-1, 0, 0, N, 0, M, std::vector<KEnt>(), sx, sy);
   if (B.status) return MRA_BUILD_UNSUPPORTED;
   const int nn = (int)B.rec.size();
   if (nn > max_nodes) return MRA_ERR_NOMEM;

@@ -9,7 +9,7 @@ from pymra_b200.structure import build_structure, build_structure_native
 
 CASES = [(40, 40, 8, 2, 5), (50, 50, 16, 2, 6), (33, 47, 5, 2, 7), (64, 64, 8, 3, 8), (96, 96, 16, 3, 12),
          (125, 125, 16, 4, 5), (201, 157, 32, 3, 9), (128, 128, 64, 2, 1), (300, 300, 16, 5, 2),
-         (400, 380, 64, 3, 4), (512, 512, 128, 2, 13)]   # the last two take the reverse-traced selection on 2 levels
+         (400, 380, 64, 3, 4), (512, 512, 128, 2, 13), (700, 611, 32, 4, 21)]   # the last three take the reverse-traced selection and the threaded two-phase build (cooperative path >= 2^18 rows)
 
 
 def same(a, b):
@@ -69,3 +69,24 @@ def test_legacy_choice_clone_against_numpy():
         if st is None:
             continue
         assert np.array_equal(st.node_kinds_local[0], want)
+
+
+def test_threaded_path_on_scattered_points_and_fallback():
+    """>= 2^16 scattered points: regular tree -> threaded two-phase build; one level deeper the leaves'
+    parents fall under 100 rows -> both native paths decline and leave the RNG untouched."""
+    rng = np.random.RandomState(1)
+    locs = rng.uniform(size=(80000, 2))
+    np.random.seed(8)
+    a = build_structure(locs, 10, 5, 4, 6, native=False)
+    sa = np.random.get_state()
+    np.random.seed(8)
+    b = build_structure_native(locs, 10, 5, 4, 6)
+    sb = np.random.get_state()
+    assert b is not None
+    same(a, b)
+    assert np.array_equal(sa[1], sb[1]) and sa[2] == sb[2]
+    np.random.seed(8)
+    s0 = np.random.get_state()
+    assert build_structure_native(locs, 10, 6, 4, 7) is None
+    s1 = np.random.get_state()
+    assert np.array_equal(s0[1], s1[1]) and s0[2] == s1[2]
