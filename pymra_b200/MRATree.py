@@ -100,7 +100,8 @@ class MRATree(object):
         obs_arr = np.asarray(obs, dtype=np.float64)
         if obs_arr.shape != (N, 1):
             raise ValueError("obs must have shape (N, 1) (the reference wraps it in np.matrix, MRATree.py:61)")
-        self.obs_inds = np.where(np.logical_not(np.isnan(obs)))[0]
+        self._obs_ref = obs
+        self._obs_inds = None
         self._cov = introspect(cov, self.d)
         self._R = float(R)
         logger.debug("r: %d, \tJ: %d,\tM: %d" % (self.r, self.J, self.M))
@@ -118,6 +119,13 @@ class MRATree(object):
         t4 = time.perf_counter()
         self.timings.update(args_and_cov=t1 - t0, structure=t2 - t1, session_plan_upload=t3 - t2,
                             likelihood=t4 - t3, **self._session.timings)
+
+    @property
+    def obs_inds(self):
+        """MRATree.py:62, evaluated on first use (it is an O(N) scan no part of the hot path needs)."""
+        if self._obs_inds is None:
+            self._obs_inds = np.where(np.logical_not(np.isnan(self._obs_ref)))[0]
+        return self._obs_inds
 
     # ---- plumbing
     def _evaluate(self):

@@ -61,7 +61,7 @@ def _solve_matern_t(g):
     return t
 
 
-def introspect(cov, d, rtol=1e-12, n_check=512, seed=12345):
+def introspect(cov, d, rtol=1e-12, n_check=192, seed=12345):
     """Return the CovDescriptor of `cov`, or raise ValueError / NotImplementedError."""
     if isinstance(cov, CovDescriptor):
         return cov

@@ -30,7 +30,7 @@ struct Arena {
 
 struct Layout {
   size_t nodes, knot_rows, obs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
-      mean, var, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks, ltiles;
+      mean, var, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks, ltiles, GTF, UTF, fold;
   size_t total;
 };
 
@@ -54,6 +54,7 @@ struct mra_handle {
   std::vector<std::vector<int4>> ptiles_at;    // prior pass: the same plus gathered knot tiles (sharded runs)
   std::vector<int> gather_rows;                // row ids of the gathered tiles
   std::vector<int4> leaf_tiles;                // 64-row tiles of leaves / orphans (fused predict pass)
+  std::vector<int4> fold_items;                // (node, ancestor level, row tile, column tile) of k_fold
   std::vector<int2> emit_chunks;               // row ranges whose results this rank emits
   // subtree sharding (mra_set_shard): role per node, 0 = another rank's, 1 = mine, 2 = replicated top,
   // 3 = replicated top whose rows this rank emits
@@ -146,6 +147,8 @@ DevCtx make_ctx(mra_handle* h) {
   c.QT = at<double>(h, L.QT);
   c.A = at<double>(h, L.A);
   c.GT = at<double>(h, L.GT);
+  c.GTF = at<double>(h, L.GTF);
+  c.UTF = at<double>(h, L.UTF);
   c.LPINV = at<double>(h, L.LPINV);
   c.VK = at<double>(h, L.VK);
   c.LINV = at<double>(h, L.LINV);
@@ -200,6 +203,7 @@ cudaError_t configure_vec(int r) {
   SET_(k_assemble_A<V_>, smem_plain());
   SET_(k_node_factor<V_>, smem_factor(r));
   SET_(k_predict_fused<V_>, smem_predict(r));
+  SET_(k_fold<V_>, smem_plain());
 #undef SET_
   return cudaSuccess;
 }
@@ -374,6 +378,9 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
       dim3 g2(nleaf, nbr);
       MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", k_leaf_solve<V_><<<g2, NT, smem_solve(), st>>>(c, leaf_list, 1)));
     }
+    if (!h->fold_items.empty())
+      MRA_FOR_VEC(h, LAUNCH("fold", k_fold<V_><<<(unsigned)h->fold_items.size(), NT, smem_plain(), st>>>(
+                                        c, at<int4>(h, L.fold))));
     if (!h->leaf_tiles.empty())
       MRA_FOR_VEC(h, LAUNCH("predict_fused", k_predict_fused<V_><<<(unsigned)h->leaf_tiles.size(), NT, smem_predict(r), st>>>(
                                                  c, at<int4>(h, L.ltiles))));
@@ -660,11 +667,28 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
     }
   }
   h->n_obs_total = (int64_t)h->obs_rows.size();
+  h->fold_items.clear();
+  if (h->want_predict) {
+    const int nct = (r + TB - 1) / TB;
+    for (int n = 0; n < nn; ++n) {
+      const NodeDev& d = h->nodes[n];
+      if (!h->role[n] || d.level < 1) continue;
+      int nxt;
+      if (d.kind == KIND_INTERNAL) nxt = nct;
+      else if (d.kind == KIND_LEAF && d.n_obs > 0) nxt = (d.n_obs + TB - 1) / TB;
+      else continue;
+      for (int j = 0; j < d.level; ++j)
+        for (int ct = 0; ct < nct; ++ct)
+          for (int xt = 0; xt < nxt; ++xt) h->fold_items.push_back(make_int4(n, j, ct, xt));
+      const double cols = d.kind == KIND_INTERNAL ? r : d.n_obs;
+      add_work(h, "fold", 2.0 * d.level * (double)r * r * cols, 8.0 * 2.0 * d.level * r * cols);
+    }
+  }
   add_work(h, "unpermute", 0.0, 8.0 * 4.0 * (double)h->N);
   h->flops_lik = h->flops_pred = 0.0;
   for (size_t i = 0; i < h->kname.size(); ++i) {
     const std::string& nm = h->kname[i];
-    const bool pred = nm == "leaf_gram_T" || nm == "leaf_solve_Q" || nm == "predict_fused" || nm == "unpermute";
+    const bool pred = nm == "leaf_gram_T" || nm == "leaf_solve_Q" || nm == "fold" || nm == "predict_fused" || nm == "unpermute";
     (pred ? h->flops_pred : h->flops_lik) += h->kflops[i];
   }
   // ---- arena layout
@@ -683,6 +707,8 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.DI = ar.take(D * std::max<long long>(1, di_off));
   L.UT = ar.take(D * std::max<long long>(1, ut_off));
   L.QT = ar.take(D * std::max<long long>(1, qt_off));
+  L.UTF = ar.take(D * std::max<long long>(1, h->want_predict ? ut_off : 0));
+  L.GTF = ar.take(D * std::max<long long>(1, h->want_predict ? gt_off : 0));
   L.A = ar.take(D * std::max<long long>(1, a_off));
   L.GT = ar.take(D * std::max<long long>(1, gt_off));
   L.LPINV = ar.take(D * std::max<long long>(1, lp_off));
@@ -719,6 +745,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.gather = ar.take(std::max<size_t>(256, sizeof(int) * h->gather_rows.size()));
   L.chunks = ar.take(std::max<size_t>(256, sizeof(int2) * h->emit_chunks.size()));
   L.ltiles = ar.take(std::max<size_t>(256, sizeof(int4) * h->leaf_tiles.size()));
+  L.fold = ar.take(std::max<size_t>(256, sizeof(int4) * h->fold_items.size()));
   L.total = ar.off;
   *workspace_bytes = L.total;
   h->planned = true;
@@ -773,6 +800,9 @@ int mra_upload_data(mra_handle* h, const double* locs, const double* obs, void* 
                        cudaMemcpyHostToDevice, st));
   if (!h->leaf_tiles.empty())
     CU(cudaMemcpyAsync(h->ws + L.ltiles, h->leaf_tiles.data(), sizeof(int4) * h->leaf_tiles.size(),
+                       cudaMemcpyHostToDevice, st));
+  if (!h->fold_items.empty())
+    CU(cudaMemcpyAsync(h->ws + L.fold, h->fold_items.data(), sizeof(int4) * h->fold_items.size(),
                        cudaMemcpyHostToDevice, st));
   if (!h->emit_chunks.empty())
     CU(cudaMemcpyAsync(h->ws + L.chunks, h->emit_chunks.data(), sizeof(int2) * h->emit_chunks.size(),

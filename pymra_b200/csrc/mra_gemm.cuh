@@ -248,6 +248,69 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
   cp_async_wait<0>();
 }
 
+// Position of element (k-row kr, column n) of a staged K-major 16 x 64 chunk (B given as B[k][n]).
+__device__ __forceinline__ int kstage_pos(int kr, int n) { return kr * TB + (n ^ ((kr & 3) << 2)); }
+
+// acc += A * B with A K-contiguous rows in global memory (fa(rr) -> row pointer) and B K-major in global
+// memory: B[k][n] = bbase[k * ldb + n], k < K, n < ncols (zero outside).  Used where the contraction index
+// is the row index of a stored block (left-multiplication of a block by a small matrix).
+template <int VEC, class FA>
+__device__ __forceinline__ void tile_gemm_kmajorB(Acc& acc, int K, FA fa, const double* bbase, long long ldb,
+                                                  int ncols, GemmSmem& sm, const double* dummy) {
+  __syncthreads();
+  if (threadIdx.x < TB) sm.row_a[0][threadIdx.x] = fa((int)threadIdx.x);
+  __syncthreads();
+  auto load_b = [&](double* st, int k0) {
+    if (VEC == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int cch = threadIdx.x + NT * i;
+        const int kr = cch >> 5, n0 = (cch & 31) * 2, k = k0 + kr;
+        const int nv = k < K ? min(max(ncols - n0, 0), 2) * 8 : 0;
+        cp_async_16(st + kstage_pos(kr, n0), nv ? bbase + (size_t)k * ldb + n0 : dummy, nv);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int cch = threadIdx.x + NT * i;
+        const int kr = cch >> 6, n = cch & 63, k = k0 + kr;
+        const int nv = (k < K && n < ncols) ? 8 : 0;
+        cp_async_8(st + kstage_pos(kr, n), nv ? bbase + (size_t)k * ldb + n : dummy, nv);
+      }
+    }
+  };
+  const int nk = (K + KC - 1) / KC;
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) {
+    if (s < nk) {
+      stage_load<VEC>(sm.a[s], sm.row_a[0], s * KC, K, dummy);
+      load_b(sm.b[s], s * KC);
+    }
+    cp_async_commit();
+  }
+  int buf = 0;
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();
+    {
+      const int kn = kt + NSTAGE - 1;
+      int nb = buf + NSTAGE - 1;
+      if (nb >= NSTAGE) nb -= NSTAGE;
+      if (kn < nk) {
+        stage_load<VEC>(sm.a[nb], sm.row_a[0], kn * KC, K, dummy);
+        load_b(sm.b[nb], kn * KC);
+      }
+      cp_async_commit();
+    }
+    const double* sa = sm.a[buf];
+    const double* sb = sm.b[buf];
+    chunk_mma(acc, [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; },
+              [&](int col, int kk) -> double { return sb[kstage_pos(kk, col)]; });
+    if (++buf == NSTAGE) buf = 0;
+  }
+  cp_async_wait<0>();
+}
+
 // out += Areg * B^T where Areg is a 64 x 64 tile held in accumulator layout (columns >= K must be zero
 // or K a multiple of 4 covering them) and K <= 64.  B_GLOBAL: fb(rr) -> row pointer, streamed through the
 // cp.async stages; else fb(rr, k) -> element of a shared-memory resident operand.
