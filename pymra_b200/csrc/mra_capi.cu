@@ -30,7 +30,7 @@ struct Arena {
 
 struct Layout {
   size_t nodes, knot_rows, obs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
-      mean, var, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks, ltiles, GTF, UTF, fold;
+      mean, var, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks, ltiles, GTF, UTF, fold, VKL;
   size_t total;
 };
 
@@ -151,6 +151,7 @@ DevCtx make_ctx(mra_handle* h) {
   c.UTF = at<double>(h, L.UTF);
   c.LPINV = at<double>(h, L.LPINV);
   c.VK = at<double>(h, L.VK);
+  c.VKL = at<double>(h, L.VKL);
   c.LINV = at<double>(h, L.LINV);
   c.dnode = at<double>(h, L.dnode);
   c.mean = at<double>(h, L.mean);
@@ -163,10 +164,7 @@ DevCtx make_ctx(mra_handle* h) {
 
 constexpr size_t GS = sizeof(GemmSmem);
 size_t smem_knot(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + 3 * r + NT * 9) + sizeof(int) * r + 16; }
-size_t smem_prior(int r) {
-  int ldT = ((r + 15) / 16) * 16 + 4;
-  return GS + sizeof(double) * ((size_t)(r > TB ? TB * ldT : 0) + 2 * r + 2 * TB) + sizeof(int) * TB;
-}
+size_t smem_prior(int r) { return GS + sizeof(double) * ((size_t)2 * r + 2 * TB) + sizeof(int) * TB; }
 size_t smem_gram() { return GS + sizeof(int) * 2 * TB; }
 size_t smem_chol() { return GS + sizeof(double) * ((size_t)TB * LDB + TB + NT * 9); }
 size_t smem_solve() { return GS; }
@@ -713,6 +711,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.GT = ar.take(D * std::max<long long>(1, gt_off));
   L.LPINV = ar.take(D * std::max<long long>(1, lp_off));
   L.VK = ar.take(D * std::max<long long>(1, vk_off));
+  L.VKL = ar.take(D * std::max<long long>(1, vk_off));
   L.LINV = ar.take(D * std::max<long long>(1, linv_off));
   L.dnode = ar.take(D * nn);
   L.mean = ar.take(D * N);

@@ -198,13 +198,22 @@ __device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSme
 // acc += sum_s A_s B_s^T over up to MAXSEG K-segments, all operands in global memory, as ONE pipelined
 // stream of chunks (no pipeline drain between segments).  fa(s, rr) / fb(s, rr) -> row pointer of tile row
 // rr in segment s (nullptr = zero row), fk(s) -> K of segment s (may be 0).
-template <int VEC, class FA, class FB, class FK>
+// GEN: the A operand of the LAST segment is not loaded but computed, fg(row, k) -> element (e.g. a covariance
+// tile evaluated on the fly); its chunks are written straight into the pipeline stages.
+struct NoGen {
+  __device__ double operator()(int, int) const { return 0.0; }
+};
+
+template <int VEC, bool GEN = false, class FA, class FB, class FK, class FG = NoGen>
 __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, FK fk, GemmSmem& sm,
-                                              const double* dummy, int mrows = TB, int ncols = TB) {
+                                              const double* dummy, int mrows = TB, int ncols = TB, FG fg = FG()) {
   __syncthreads();
   for (int s = 0; s < nseg; ++s) {
-    if (threadIdx.x < TB) sm.row_a[s][threadIdx.x] = fa(s, (int)threadIdx.x);
-    else sm.row_b[s][threadIdx.x - TB] = fb(s, (int)threadIdx.x - TB);
+    if (threadIdx.x < TB) {
+      if (!(GEN && s == nseg - 1)) sm.row_a[s][threadIdx.x] = fa(s, (int)threadIdx.x);
+    } else {
+      sm.row_b[s][threadIdx.x - TB] = fb(s, (int)threadIdx.x - TB);
+    }
     if (threadIdx.x == 0) sm.seg_k[s] = fk(s);
   }
   __syncthreads();
@@ -219,7 +228,20 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
     }
     if (lseg < nseg) {
       const int K = sm.seg_k[lseg];
-      stage_load<VEC>(sm.a[buf], sm.row_a[lseg], lk0, K, dummy);
+      if (GEN && lseg == nseg - 1) {
+        const int kc = (threadIdx.x & 7) * 2, rb = threadIdx.x >> 3;
+        const int k = lk0 + kc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = rb + 16 * i;
+          double2 v;
+          v.x = k < K ? fg(row, k) : 0.0;
+          v.y = k + 1 < K ? fg(row, k + 1) : 0.0;
+          *reinterpret_cast<double2*>(sm.a[buf] + stage_pos(row, kc)) = v;
+        }
+      } else {
+        stage_load<VEC>(sm.a[buf], sm.row_a[lseg], lk0, K, dummy);
+      }
       stage_load<VEC>(sm.b[buf], sm.row_b[lseg], lk0, K, dummy);
       lk0 += KC;
     }
