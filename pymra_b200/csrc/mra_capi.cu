@@ -166,7 +166,7 @@ constexpr size_t GS = sizeof(GemmSmem);
 size_t smem_knot(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + 3 * r + NT * 9) + sizeof(int) * r + 16; }
 size_t smem_prior(int r) { return GS + sizeof(double) * ((size_t)2 * r + 2 * TB) + sizeof(int) * TB; }
 size_t smem_gram() { return GS + sizeof(int) * 2 * TB; }
-size_t smem_chol() { return GS + sizeof(double) * ((size_t)TB * LDB + TB + NT * 9); }
+size_t smem_chol(int max_obs) { return GS + sizeof(double) * ((size_t)TB * LDB + TB + NT * 9 + TB + ((max_obs + TB - 1) / TB) * TB); }
 size_t smem_solve() { return GS; }
 size_t smem_plain() { return GS; }
 size_t smem_factor(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + r + NT * 9); }
@@ -188,7 +188,7 @@ size_t smem_predict(int r) {
   } while (0)
 
 template <int V_>
-cudaError_t configure_vec(int r) {
+cudaError_t configure_vec(int r, int max_obs) {
   cudaError_t e;
 #define SET_(k, bytes)                                                                         \
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));      \
@@ -196,7 +196,7 @@ cudaError_t configure_vec(int r) {
   SET_(k_knot_factor<V_>, smem_knot(r));
   SET_(k_prior_tiles<V_>, smem_prior(r));
   SET_(k_leaf_gram<V_>, smem_gram());
-  SET_(k_leaf_factor<V_>, smem_chol());
+  SET_(k_leaf_factor<V_>, smem_chol(max_obs));
   SET_(k_leaf_solve<V_>, smem_solve());
   SET_(k_assemble_A<V_>, smem_plain());
   SET_(k_node_factor<V_>, smem_factor(r));
@@ -207,7 +207,9 @@ cudaError_t configure_vec(int r) {
 }
 
 int configure_kernels(mra_handle* h) {
-  MRA_FOR_VEC(h, CU(configure_vec<V_>(h->r)));
+  if (smem_chol(h->max_leaf_obs) > 200 * 1024)
+    return fail(h, MRA_ERR_ARG, "a leaf has too many observations for this build");
+  MRA_FOR_VEC(h, CU(configure_vec<V_>(h->r, h->max_leaf_obs)));
   return MRA_OK;
 }
 
@@ -281,9 +283,9 @@ int upward_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m) {
   const int nn = (int)h->internal_at[m].size();
   if (!nn) return MRA_OK;
   const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
-  const int W = (m + 1) * r + 1, nb = (W + TB - 1) / TB;
-  dim3 ga(nn, nb * (nb + 1) / 2);
-  MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<ga, NT, smem_plain(), st>>>(c, list, nullptr, 0)));
+  const int W = (m + 1) * r + 1, nb = (W - 1 + TB - 1) / TB;
+  const int nt = nb * (nb + 1) / 2 + 1;   // lower tile pairs of the basis block + the augmented-row job
+  MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<(unsigned)nn * nt, NT, smem_plain(), st>>>(c, list, nullptr, 0, nt)));
   MRA_FOR_VEC(h, LAUNCH("node_factor", k_node_factor<V_><<<nn, NT, smem_factor(r), st>>>(c, list)));
   return MRA_OK;
 }
@@ -313,11 +315,11 @@ int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary)
   const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off);
   if (nleaf && h->max_leaf_obs > 0) {
     const int nbo = (h->max_leaf_obs + TB - 1) / TB;
-    dim3 g1(nleaf, nbo * (nbo + 1) / 2);
-    MRA_FOR_VEC(h, LAUNCH("leaf_gram", k_leaf_gram<V_><<<g1, NT, smem_gram(), st>>>(c, leaf_list, 0)));
-    MRA_FOR_VEC(h, LAUNCH("leaf_chol", k_leaf_factor<V_><<<nleaf, NT, smem_chol(), st>>>(c, leaf_list)));
-    dim3 g3(nleaf, (h->max_leaf_W + TB - 1) / TB);
-    MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve<V_><<<g3, NT, smem_solve(), st>>>(c, leaf_list, 0)));
+    const int nt1 = nbo * (nbo + 1) / 2;
+    MRA_FOR_VEC(h, LAUNCH("leaf_gram", k_leaf_gram<V_><<<(unsigned)nleaf * nt1, NT, smem_gram(), st>>>(c, leaf_list, 0, nt1)));
+    MRA_FOR_VEC(h, LAUNCH("leaf_chol", k_leaf_factor<V_><<<nleaf, NT, smem_chol(h->max_leaf_obs), st>>>(c, leaf_list)));
+    const int nt3 = std::max(1, (h->max_leaf_W - 1 + TB - 1) / TB);
+    MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve<V_><<<(unsigned)nleaf * nt3, NT, smem_solve(), st>>>(c, leaf_list, 0, nt3)));
   }
   // ---- upward, levels >= shard level
   for (int m = (int)h->internal_at.size() - 1; m >= h->shard_level; --m) {
@@ -326,10 +328,10 @@ int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary)
   }
   if (h->shard_level > 0 && !h->sroots.empty()) {
     const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->sroots_off);
-    const int W = h->shard_level * r + 1, nb = (W + TB - 1) / TB;
-    dim3 ga((unsigned)h->sroots.size(), nb * (nb + 1) / 2);
-    MRA_FOR_VEC(h, LAUNCH("export_summary",
-                          k_assemble_A<V_><<<ga, NT, smem_plain(), st>>>(c, list, dev_summary, h->slot_base)));
+    const int W = h->shard_level * r + 1, nb = (W - 1 + TB - 1) / TB;
+    const int nt = nb * (nb + 1) / 2 + 1;
+    MRA_FOR_VEC(h, LAUNCH("export_summary", k_assemble_A<V_><<<(unsigned)h->sroots.size() * nt, NT, smem_plain(), st>>>(
+                                                c, list, dev_summary, h->slot_base, nt)));
   }
   CU(cudaGetLastError());
   return MRA_OK;
@@ -371,10 +373,10 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
     const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off);
     if (h->max_leaf_obs > 0) {
       const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
-      dim3 g1(nleaf, nbr * nbo);
-      MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<g1, NT, smem_gram(), st>>>(c, leaf_list, 1)));
-      dim3 g2(nleaf, nbr);
-      MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", k_leaf_solve<V_><<<g2, NT, smem_solve(), st>>>(c, leaf_list, 1)));
+      MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<(unsigned)nleaf * nbr * nbo, NT, smem_gram(), st>>>(
+                                               c, leaf_list, 1, nbr * nbo)));
+      MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", k_leaf_solve<V_><<<(unsigned)nleaf * nbr, NT, smem_solve(), st>>>(
+                                                c, leaf_list, 1, nbr)));
     }
     if (!h->fold_items.empty())
       MRA_FOR_VEC(h, LAUNCH("fold", k_fold<V_><<<(unsigned)h->fold_items.size(), NT, smem_plain(), st>>>(
