@@ -242,7 +242,7 @@ def run_ours(args, rank, world, local_rank):
     for i in range(1 + e2e_steps):
         barrier()
         t0 = time.time()
-        tree = MRATree(locs, r, cov, obs, R, M=Mreq, group=group)
+        tree = MRATree(locs, r, cov, obs, R, M=Mreq, group=group, gather="root")
         lik_e2e = float(np.asarray(tree.getLikelihood()).ravel()[0])
         mean_h, sd_h = tree.predict()
         barrier()

@@ -11,7 +11,7 @@ PyTorch only supplies the device arena and the stream.  There is no CPU fallback
 Beyond the reference signature: `device` (CUDA ordinal) and `group` (a torch.distributed process group,
 or True for the default one): every rank of the group constructs the same tree from the same inputs and
 RNG state, whole subtrees are sharded over the ranks' GPUs (pymra_b200/shard.py), and every rank returns
-the full likelihood and predictions.
+the full likelihood and predictions (gather="root": predictions only on rank 0, None elsewhere).
 """
 import logging
 import time
@@ -81,7 +81,8 @@ class _Root(object):
 
 class MRATree(object):
 
-    def __init__(self, locs, r, cov, obs, R, M=-1, J=-1, critDepth=-1, verbose=True, device=None, group=None):
+    def __init__(self, locs, r, cov, obs, R, M=-1, J=-1, critDepth=-1, verbose=True, device=None, group=None,
+                 gather="all"):
         t0 = time.perf_counter()
         self.timings = {}          # host-side wall-clock breakdown of this construction (seconds)
         self.locs = locs
@@ -111,7 +112,8 @@ class MRATree(object):
         t1 = time.perf_counter()
         self._structure = build_structure(locs_c, r, M, J, critDepth)
         t2 = time.perf_counter()
-        self._session = DeviceSession(self._structure, locs_c, obs_arr, want_predict=True, device=device, group=group)
+        self._session = DeviceSession(self._structure, locs_c, obs_arr, want_predict=True, device=device, group=group,
+                                      gather=gather)
         t3 = time.perf_counter()
         self._mom = None
         self._evaluate()
@@ -137,7 +139,10 @@ class MRATree(object):
         if self._mom is None:
             t0 = time.perf_counter()
             mean, sd = self._session.predict()
-            self._mom = (np.matrix(mean.reshape(-1, 1)), sd * sd, sd)
+            if mean is None:            # sharded run with gather="root" on a non-root rank
+                self._mom = (None, None, None)
+            else:
+                self._mom = (np.matrix(mean.reshape(-1, 1)), sd * sd, sd)
             self.timings["predict"] = time.perf_counter() - t0
         return self._mom
 

@@ -74,7 +74,7 @@ struct mra_handle {
   size_t ws_bytes = 0;
   std::vector<size_t> list_off, tiles_off, ptiles_off;   // per level offsets (bytes) inside lay.lists / lay.tiles / lay.ptiles
   size_t leaves_off = 0;
-  CovParams cov{0, 1.0, 1.0, 1.0};
+  CovParams cov{0, 1.0, 1.0, 1.0, 1.0};
   double R = 1.0;
   bool cov_set = false, R_set = false;
   int64_t launches = 0;
@@ -284,8 +284,8 @@ int upward_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m) {
   if (!nn) return MRA_OK;
   const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
   const int W = (m + 1) * r + 1, nb = (W - 1 + TB - 1) / TB;
-  const int nt = nb * (nb + 1) / 2 + 1;   // lower tile pairs of the basis block + the augmented-row job
-  MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<(unsigned)nn * nt, NT, smem_plain(), st>>>(c, list, nullptr, 0, nt)));
+  const int nt = nb * (nb + 1) / 2 + (W + TB - 1) / TB;   // lower tile pairs of the basis block + augmented-row jobs
+  MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<(unsigned)nn * nt, NT, smem_plain(), st>>>(c, list, nullptr, 0, nn)));
   MRA_FOR_VEC(h, LAUNCH("node_factor", k_node_factor<V_><<<nn, NT, smem_factor(r), st>>>(c, list)));
   return MRA_OK;
 }
@@ -316,7 +316,7 @@ int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary)
   if (nleaf && h->max_leaf_obs > 0) {
     const int nbo = (h->max_leaf_obs + TB - 1) / TB;
     const int nt1 = nbo * (nbo + 1) / 2;
-    MRA_FOR_VEC(h, LAUNCH("leaf_gram", k_leaf_gram<V_><<<(unsigned)nleaf * nt1, NT, smem_gram(), st>>>(c, leaf_list, 0, nt1)));
+    MRA_FOR_VEC(h, LAUNCH("leaf_gram", k_leaf_gram<V_><<<(unsigned)nleaf * nt1, NT, smem_gram(), st>>>(c, leaf_list, 0, nleaf)));
     MRA_FOR_VEC(h, LAUNCH("leaf_chol", k_leaf_factor<V_><<<nleaf, NT, smem_chol(h->max_leaf_obs), st>>>(c, leaf_list)));
     const int nt3 = std::max(1, (h->max_leaf_W - 1 + TB - 1) / TB);
     MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve<V_><<<(unsigned)nleaf * nt3, NT, smem_solve(), st>>>(c, leaf_list, 0, nt3)));
@@ -329,9 +329,9 @@ int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary)
   if (h->shard_level > 0 && !h->sroots.empty()) {
     const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->sroots_off);
     const int W = h->shard_level * r + 1, nb = (W - 1 + TB - 1) / TB;
-    const int nt = nb * (nb + 1) / 2 + 1;
+    const int nt = nb * (nb + 1) / 2 + (W + TB - 1) / TB;
     MRA_FOR_VEC(h, LAUNCH("export_summary", k_assemble_A<V_><<<(unsigned)h->sroots.size() * nt, NT, smem_plain(), st>>>(
-                                                c, list, dev_summary, h->slot_base, nt)));
+                                                c, list, dev_summary, h->slot_base, (int)h->sroots.size())));
   }
   CU(cudaGetLastError());
   return MRA_OK;
@@ -374,7 +374,7 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
     if (h->max_leaf_obs > 0) {
       const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
       MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<(unsigned)nleaf * nbr * nbo, NT, smem_gram(), st>>>(
-                                               c, leaf_list, 1, nbr * nbo)));
+                                               c, leaf_list, 1, nleaf)));
       MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", k_leaf_solve<V_><<<(unsigned)nleaf * nbr, NT, smem_solve(), st>>>(
                                                 c, leaf_list, 1, nbr)));
     }
@@ -831,6 +831,7 @@ int mra_set_cov(mra_handle* h, int family, double length_scale, double sig) {
   h->cov.l = length_scale;
   h->cov.sig = sig;
   h->cov.c0 = h->cov.sig;
+  h->cov.a = (family == MRA_COV_EXP ? 1.0 : 1.7320508075688772) / length_scale;
   h->cov_set = true;
   h->lik_done = h->pred_done = false;
   return MRA_OK;

@@ -21,7 +21,8 @@ def _dptr(a):
 
 
 class DeviceSession(object):
-    def __init__(self, structure, locs, obs, want_predict=True, device=None, group=None, emulate=None):
+    def __init__(self, structure, locs, obs, want_predict=True, device=None, group=None, emulate=None,
+                 gather="all"):
         """group: a torch.distributed process group (or True for the default group) to shard whole
         subtrees across its ranks, one GPU per rank (pymra_b200/shard.py); None = single GPU.
         emulate=(world, rank): build the shard of `rank` without a process group; the caller drives
@@ -40,6 +41,7 @@ class DeviceSession(object):
         self._set_structure()
         self.timings["set_structure"] = time.perf_counter() - t0
         self.group, self.world, self.rank, self.shard_level, self.summary = None, 1, 0, 0, None
+        self.gather = gather        # sharded predict(): "all" = every rank gets all N results, "root" = rank 0 only
         if group is not None or emulate is not None:
             from .shard import plan_shards
             if emulate is not None:
@@ -140,11 +142,21 @@ class DeviceSession(object):
     def predict(self):
         if self.shard_level:
             import torch
+            import torch.distributed as dist
             out = torch.empty(2, self.N, dtype=torch.float64, device=self.dev)
-            self.predict_dev(out[0], out[1], reduce=True)
-            host = out.cpu().numpy()
+            self.predict_dev(out[0], out[1])
+            if self.gather == "root":
+                dist.reduce(out, dst=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                            group=self.group)
+            else:
+                dist.all_reduce(out, group=self.group)
             self.fetch_likelihood()                           # surfaces a non-SPD status like the plain path
-            return host[0].copy(), host[1].copy()
+            if self.gather == "root" and self.rank != 0:
+                return None, None
+            host = torch.empty(2, self.N, dtype=torch.float64, pin_memory=True)
+            host.copy_(out)
+            res = host.numpy()
+            return res[0], res[1]
         # page-locked staging (torch's caching host allocator): the device->host copy runs at PCIe rate and the
         # returned arrays are zero-copy views of it
         import torch
