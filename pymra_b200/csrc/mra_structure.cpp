@@ -31,7 +31,7 @@ struct MT {
   int pos;
   uint32_t out[624];
   bool out_valid = false;
-  void gen() {
+  __attribute__((target_clones("avx2", "default"))) void gen() {
     const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, MA = 0x9908b0dfu;
     int kk;
     uint32_t y;
@@ -48,7 +48,7 @@ struct MT {
     pos = 0;
     out_valid = false;
   }
-  void temper_all() {
+  __attribute__((target_clones("avx2", "default"))) void temper_all() {
     for (int i = 0; i < 624; ++i) {
       uint32_t y = key[i];
       y ^= (y >> 11);

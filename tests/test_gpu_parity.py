@@ -60,3 +60,32 @@ def test_errors_cross_the_abi_as_exceptions():
         MRATree(g["locs"], 8, lambda a, b: mt.ExpCovFun(a, b, l=0.3), g["obs"], np.eye(len(g["locs"])))
     with pytest.raises(ValueError):
         MRATree(g["locs"], 8, lambda a, b: mt.ExpCovFun(a, b, l=0.3), g["obs"].ravel(), 1e-2)
+
+
+@pytest.mark.parametrize("n,M,r,family,frac", [(64, 1, 80, "matern32", 0.4),     # r > 64: two column tiles per block
+                                                (80, 2, 64, "exp", 0.4),          # the headline r
+                                                (72, 2, 33, "matern32", 0.5),     # odd r: 8-byte copy path
+                                                (64, 1, 128, "exp", 0.3)])        # largest r of this build
+def test_large_r_against_oracle(n, M, r, family, frac):
+    """Knot counts no committed reference fixture covers, checked against the oracle on the same seeded inputs
+    (likelihood 1e-9 relative, mean 1e-9 absolute (unit-scale field), sd 1e-8 relative: the oracle's own noise)."""
+    import pymra_b200.MRATools as mt
+    from oracle.mra_oracle import mra_oracle
+    from pymra_b200.MRATree import MRATree
+    locs = mt.genLocations2d(n)
+    rng = np.random.RandomState(n + r)
+    y = np.sin(6 * locs[:, :1]) * np.cos(4 * locs[:, 1:]) + 0.2 * rng.normal(size=(len(locs), 1))
+    obs = np.full_like(y, np.nan)
+    sel = np.sort(rng.choice(len(locs), int(frac * len(locs)), replace=False))
+    obs[sel] = y[sel]
+    l, sig, R = 0.3, 1.0, 1e-2
+    cov = (lambda a, b: mt.ExpCovFun(a, b, l=l)) if family == "exp" else (lambda a, b: mt.Matern32(a, b, l=l, sig=sig))
+    np.random.seed(7)
+    t = MRATree(locs, r, cov, obs, R, M=M)
+    lik = float(np.asarray(t.getLikelihood()).ravel()[0])
+    mean, sd = t.predict()
+    np.random.seed(7)
+    o = mra_oracle(locs, r, family, l, sig, obs, R, M=M)
+    assert abs(lik - o["lik"]) <= 1e-9 * abs(o["lik"]), (lik, o["lik"])
+    assert np.max(np.abs(np.asarray(mean).ravel() - o["mean"])) <= 1e-9
+    assert np.max(np.abs(sd - o["sd"]) / np.maximum(o["sd"], 1e-300)) <= 1e-8
