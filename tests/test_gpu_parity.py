@@ -62,14 +62,19 @@ def test_errors_cross_the_abi_as_exceptions():
         MRATree(g["locs"], 8, lambda a, b: mt.ExpCovFun(a, b, l=0.3), g["obs"].ravel(), 1e-2)
 
 
-@pytest.mark.parametrize("n,M,r,family,frac", [(64, 1, 80, "matern32", 0.4),     # r > 64: two column tiles per block
+@pytest.mark.parametrize("n,M,r,family,frac", [(64, 1, 80, "exp", 0.4),          # r > 64: two column tiles per block
+                                                (64, 1, 80, "matern32", 0.4),     # same, ill-conditioned (floor applies)
                                                 (80, 2, 64, "exp", 0.4),          # the headline r
-                                                (72, 2, 33, "matern32", 0.5),     # odd r: 8-byte copy path
+                                                (72, 2, 33, "exp", 0.5),          # odd r: 8-byte copy path
+                                                (72, 2, 33, "matern32", 0.5),
                                                 (64, 1, 128, "exp", 0.3)])        # largest r of this build
 def test_large_r_against_oracle(n, M, r, family, frac):
-    """Knot counts no committed reference fixture covers, checked against the oracle on the same seeded inputs
-    (likelihood 1e-9 relative, mean 1e-9 absolute (unit-scale field), sd 1e-8 relative: the oracle's own noise)."""
+    """Knot counts no committed reference fixture covers, checked against the oracle on the same seeded inputs.
+    Tolerance: 1e-9 (likelihood relative, mean absolute on a unit-scale field, sd relative) or, where two
+    independent FP64 CPU evaluations of the same quantities (oracle recursion vs the dual-form NumPy model,
+    tests/_model.py) already differ by more, 20x that gap -- the conditioning noise floor."""
     import pymra_b200.MRATools as mt
+    from _model import model_run
     from oracle.mra_oracle import mra_oracle
     from pymra_b200.MRATree import MRATree
     locs = mt.genLocations2d(n)
@@ -86,6 +91,9 @@ def test_large_r_against_oracle(n, M, r, family, frac):
     mean, sd = t.predict()
     np.random.seed(7)
     o = mra_oracle(locs, r, family, l, sig, obs, R, M=M)
-    assert abs(lik - o["lik"]) <= 1e-9 * abs(o["lik"]), (lik, o["lik"])
-    assert np.max(np.abs(np.asarray(mean).ravel() - o["mean"])) <= 1e-9
-    assert np.max(np.abs(sd - o["sd"]) / np.maximum(o["sd"], 1e-300)) <= 1e-8
+    mod = model_run(t._structure, locs, obs, family, l, sig, R)
+    fl, fm, fs = errs(mod["lik"], mod["mean"], mod["sd"], o)
+    rl, em, es = errs(lik, mean, sd, o)
+    assert rl <= max(1e-9, 20 * fl), ("lik", rl, fl)
+    assert em <= max(1e-9, 20 * fm), ("mean", em, fm)
+    assert es <= max(1e-9, 20 * fs), ("sd", es, fs)
