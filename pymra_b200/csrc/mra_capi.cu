@@ -30,7 +30,7 @@ struct Arena {
 
 struct Layout {
   size_t nodes, knot_rows, obs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
-      mean, var, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks, ltiles, GTF, UTF, fold, VKL;
+      mean, var, vnorm, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks, ltiles, GTF, UTF, fold, VKL;
   size_t total;
 };
 
@@ -156,6 +156,7 @@ DevCtx make_ctx(mra_handle* h) {
   c.dnode = at<double>(h, L.dnode);
   c.mean = at<double>(h, L.mean);
   c.var = at<double>(h, L.var);
+  c.vnorm = at<double>(h, L.vnorm);
   c.status = at<int>(h, L.status);
   c.cov = h->cov;
   c.R = h->R;
@@ -299,6 +300,7 @@ int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary)
   h->launches = 0;
   CU(cudaMemsetAsync(at<double>(h, L.dnode), 0, sizeof(double) * h->n_nodes, st));
   CU(cudaMemsetAsync(at<int>(h, L.status), 0, sizeof(int), st));
+  CU(cudaMemsetAsync(at<double>(h, L.vnorm), 0, sizeof(double) * h->N, st));
   // ---- prior, top-down
   for (int m = 0; m < (int)h->internal_at.size(); ++m) {
     const int nn = (int)h->internal_at[m].size();
@@ -718,6 +720,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.dnode = ar.take(D * nn);
   L.mean = ar.take(D * N);
   L.var = ar.take(D * N);
+  L.vnorm = ar.take(D * N);
   L.status = ar.take(256);
   L.out = ar.take(256);
   L.stage_locs = ar.take(D * N * h->dim);

@@ -219,8 +219,11 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
   __syncthreads();
   int nk = 0;
   for (int s = 0; s < nseg; ++s) nk += (sm.seg_k[s] + KC - 1) / KC;
-  // loader cursor
-  int lseg = 0, lk0 = 0;
+  // loader cursor; with 16-byte copies the four row pointers per operand of the current segment are kept in
+  // registers (re-read from the tables only when the segment changes)
+  int lseg = 0, lk0 = 0, cached = -1;
+  const double* pa[4];
+  const double* pb[4];
   auto load_next = [&](int buf) {
     while (lseg < nseg && lk0 >= sm.seg_k[lseg]) {
       ++lseg;
@@ -228,21 +231,47 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
     }
     if (lseg < nseg) {
       const int K = sm.seg_k[lseg];
-      if (GEN && lseg == nseg - 1) {
+      const bool gen = GEN && lseg == nseg - 1;
+      if (VEC == 2) {
         const int kc = (threadIdx.x & 7) * 2, rb = threadIdx.x >> 3;
+        if (cached != lseg) {
+          cached = lseg;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!gen) pa[i] = sm.row_a[lseg][rb + 16 * i];
+            pb[i] = sm.row_b[lseg][rb + 16 * i];
+          }
+        }
         const int k = lk0 + kc;
+        const int nv = min(max(K - k, 0), 2) * 8;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int row = rb + 16 * i;
-          double2 v;
-          v.x = k < K ? fg(row, k) : 0.0;
-          v.y = k + 1 < K ? fg(row, k + 1) : 0.0;
-          *reinterpret_cast<double2*>(sm.a[buf] + stage_pos(row, kc)) = v;
+          const int pos = stage_pos(row, kc);
+          if (gen) {
+            double2 v;
+            v.x = k < K ? fg(row, k) : 0.0;
+            v.y = k + 1 < K ? fg(row, k + 1) : 0.0;
+            *reinterpret_cast<double2*>(sm.a[buf] + pos) = v;
+          } else {
+            cp_async_16(sm.a[buf] + pos, pa[i] ? pa[i] + k : dummy, pa[i] ? nv : 0);
+          }
+          cp_async_16(sm.b[buf] + pos, pb[i] ? pb[i] + k : dummy, pb[i] ? nv : 0);
         }
       } else {
-        stage_load<VEC>(sm.a[buf], sm.row_a[lseg], lk0, K, dummy);
+        if (gen) {
+          const int kc = threadIdx.x & 15, rb = threadIdx.x >> 4;
+          const int k = lk0 + kc;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = rb + 8 * i;
+            sm.a[buf][stage_pos(row, kc)] = k < K ? fg(row, k) : 0.0;
+          }
+        } else {
+          stage_load<VEC>(sm.a[buf], sm.row_a[lseg], lk0, K, dummy);
+        }
+        stage_load<VEC>(sm.b[buf], sm.row_b[lseg], lk0, K, dummy);
       }
-      stage_load<VEC>(sm.b[buf], sm.row_b[lseg], lk0, K, dummy);
       lk0 += KC;
     }
   };
