@@ -1,6 +1,7 @@
-python tools/profile_step.py --workload cfg5 > gpurun_out/pp.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:k_predict_fused" -c 1 -o gpurun_out/pf -f python tools/profile_step.py --workload cfg5 > gpurun_out/ncu_pf.log 2>&1
-ncu -i gpurun_out/pf.ncu-rep --page source --csv > /tmp/pf_source.csv 2>/dev/null
-head -c 3000 /tmp/pf_source.csv > gpurun_out/pf_source_head.txt
-python tools/top_stalls.py 60 < /tmp/pf_source.csv > gpurun_out/pf_top_stalls.txt 2>&1
-ls -la gpurun_out/pf.ncu-rep /tmp/pf_source.csv; rm -f gpurun_out/pf.ncu-rep
+# Usage: bash tools/profile_stalls.sh <tag> <kernel regex> <skip> ; writes gpurun_out/<tag>_top_stalls.txt (small)
+TAG=$1; KRE=$2; SKIP=${3:-0}
+python tools/profile_step.py --workload cfg5 > gpurun_out/pp_$TAG.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$KRE" -s $SKIP -c 1 -o /tmp/pf_$TAG -f python tools/profile_step.py --workload cfg5 > gpurun_out/ncu_$TAG.log 2>&1
+ncu -i /tmp/pf_$TAG.ncu-rep --page source --csv > /tmp/pf_$TAG.csv 2>/dev/null
+python tools/top_stalls.py 45 < /tmp/pf_$TAG.csv > gpurun_out/${TAG}_top_stalls.txt 2>&1
+ncu -i /tmp/pf_$TAG.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/null
