@@ -271,8 +271,16 @@ def run_ours(args, rank, world, local_rank):
                       "tflops": p["flops"] / (ms * 1e-3) * 1e-12 if ms > 0 else 0.0,
                       "gbs": p["bytes"] / (ms * 1e-3) * 1e-9 if ms > 0 else 0.0}
     top = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_%s.json" % args.workload)
+    if world == 1 and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if top in tj and tj[top]["launches"]:
+            traffic = tj[top]["dram_bytes"] / tj[top]["launches"]
     roofline = {"kernel": top, "bound": "tensor", "achieved": kern[top]["tflops"], "peak": peak,
-                "unit": "TFLOP/s", "frac": kern[top]["tflops"] / peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": kern[top]["tflops"] / peak, "traffic": traffic,
+                "traffic_source": "profiles/ncu_traffic_%s.json (dram__bytes_read+write.sum per launch, ncu --set full)" % args.workload
+                if traffic is not None else None,
                 "peak_source": "cuBLAS DGEMM (torch.matmul f64, n=6144) measured in this run; "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "share_of_step": kern[top]["ms_per_step"] / (total_ms / args.steps),

@@ -88,6 +88,8 @@ struct mra_handle {
   std::vector<std::string> kname;
   std::vector<double> kflops, kbytes;   // algorithmic work per launch-group, accumulated at plan time
   std::vector<double> kms;
+  const char* memo_name[16] = {};   // add_work: literal pointer -> kernel id
+  int memo_id[16] = {};
   std::vector<int64_t> klaunch;
 };
 
@@ -163,14 +165,15 @@ DevCtx make_ctx(mra_handle* h) {
   return c;
 }
 
-constexpr size_t GS = sizeof(GemmSmem);
-size_t smem_knot(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + 3 * r + NT * 9) + sizeof(int) * r + 16; }
+constexpr size_t GS = sizeof(GemmSmem);     // kernels with segmented products
+constexpr size_t GS1 = sizeof(GemmSmem1);   // single-segment kernels
+size_t smem_knot(int r) { return GS1 + sizeof(double) * ((size_t)r * (r + 1) + 3 * r + NT * 9) + sizeof(int) * r + 16; }
 size_t smem_prior(int r) { return GS + sizeof(double) * ((size_t)2 * r + 2 * TB) + sizeof(int) * TB; }
-size_t smem_gram() { return GS + sizeof(int) * 2 * TB; }
-size_t smem_chol(int max_obs) { return GS + sizeof(double) * ((size_t)TB * LDB + TB + NT * 9 + TB + ((max_obs + TB - 1) / TB) * TB); }
-size_t smem_solve() { return GS; }
+size_t smem_gram() { return GS1 + sizeof(int) * 2 * TB; }
+size_t smem_chol(int max_obs) { return GS1 + sizeof(double) * ((size_t)TB * LDB + TB + NT * 9 + TB + ((max_obs + TB - 1) / TB) * TB); }
+size_t smem_solve() { return GS1; }
 size_t smem_plain() { return GS; }
-size_t smem_factor(int r) { return GS + sizeof(double) * ((size_t)r * (r + 1) + r + NT * 9); }
+size_t smem_factor(int r) { return GS1 + sizeof(double) * ((size_t)r * (r + 1) + r + NT * 9); }
 size_t smem_predict(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;
   return GS + sizeof(double) * ((size_t)(r > TB ? TB * ldT : 0) + 2 * TB) + sizeof(int) * MAX_LEVELS;
@@ -203,7 +206,7 @@ cudaError_t configure_vec(int r, int max_obs) {
   SET_(k_assemble_A<V_>, smem_plain());
   SET_(k_node_factor<V_>, smem_factor(r));
   SET_(k_predict_fused<V_>, smem_predict(r));
-  SET_(k_fold<V_>, smem_plain());
+  SET_(k_fold<V_>, GS1);
 #undef SET_
   return cudaSuccess;
 }
@@ -228,8 +231,16 @@ int kid(mra_handle* h, const std::string& name) {
   return id;
 }
 
-void add_work(mra_handle* h, const std::string& name, double flops, double bytes) {
-  int id = kid(h, name);
+void add_work(mra_handle* h, const char* name, double flops, double bytes) {
+  // called ~10x per node from mra_plan: memoise the id per literal (pointer identity) instead of a map lookup
+  int id = -1;
+  const unsigned slot = (unsigned)((reinterpret_cast<uintptr_t>(name) >> 3) & 15);
+  if (h->memo_name[slot] == name) id = h->memo_id[slot];
+  if (id < 0) {
+    id = kid(h, name);
+    h->memo_name[slot] = name;
+    h->memo_id[slot] = id;
+  }
   h->kflops[id] += flops;
   h->kbytes[id] += bytes;
 }
@@ -382,7 +393,7 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
                                                 c, leaf_list, nbr)));
     }
     if (!h->fold_items.empty())
-      MRA_FOR_VEC(h, LAUNCH("fold", k_fold<V_><<<(unsigned)h->fold_items.size(), NT, smem_plain(), st>>>(
+      MRA_FOR_VEC(h, LAUNCH("fold", k_fold<V_><<<(unsigned)h->fold_items.size(), NT, GS1, st>>>(
                                         c, at<int4>(h, L.fold))));
     if (!h->leaf_tiles.empty())
       MRA_FOR_VEC(h, LAUNCH("predict_fused", k_predict_fused<V_><<<(unsigned)h->leaf_tiles.size(), NT, smem_predict(r), st>>>(

@@ -25,18 +25,24 @@ namespace mra {
 constexpr int TB = 64;        // tile rows / cols
 constexpr int KC = 16;        // k chunk per pipeline stage
 constexpr int NT = 128;       // threads per CTA
-constexpr int NSTAGE = 3;     // cp.async pipeline depth
+constexpr int NSTAGE = 3;     // cp.async pipeline depth (4 was measured slower: occupancy)
 constexpr int LDB = TB + 4;   // smem row stride of a resident 64x64 block (== 4 mod 16 doubles)
 
 constexpr int MAXSEG = 8;     // K segments per tile_gemm_seg call
 
-struct GemmSmem {
+// Shared-memory working set of the tile primitive.  NS = number of K segments the row tables hold: kernels that
+// only use single-segment products take GemmSmemT<1> (49 KB -> 4 CTAs/SM), the segmented ones GemmSmemT<MAXSEG>.
+template <int NS>
+struct alignas(16) GemmSmemT {
   double a[NSTAGE][TB * KC];
   double b[NSTAGE][TB * KC];
-  const double* row_a[MAXSEG][TB];
-  const double* row_b[MAXSEG][TB];
-  int seg_k[MAXSEG];
+  const double* row_a[NS][TB];
+  const double* row_b[NS][TB];
+  int seg_k[NS];
+  int pad_[3];
 };
+using GemmSmem = GemmSmemT<MAXSEG>;
+using GemmSmem1 = GemmSmemT<1>;
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -140,8 +146,8 @@ __device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb, int mrows = TB
 //   A_GLOBAL: fa(rr) -> const double* row pointer (nullptr = zero row); else fa(rr, k) -> element
 //   (shared-memory resident operand; must return 0 for k >= K).  Same for B.
 // Must be called by all 128 threads; safe to call back to back (leading barrier).
-template <int VEC, bool A_GLOBAL, bool B_GLOBAL, class FA, class FB>
-__device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, GemmSmem& sm, const double* dummy,
+template <int VEC, bool A_GLOBAL, bool B_GLOBAL, class FA, class FB, class SM>
+__device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, SM& sm, const double* dummy,
                                           int mrows = TB, int ncols = TB) {
   __syncthreads();   // previous users of the stages / row tables (and of resident operands) are done
   if (A_GLOBAL) {
@@ -305,9 +311,9 @@ __device__ __forceinline__ int kstage_pos(int kr, int n) { return kr * TB + (n ^
 // acc += A * B with A K-contiguous rows in global memory (fa(rr) -> row pointer) and B K-major in global
 // memory: B[k][n] = bbase[k * ldb + n], k < K, n < ncols (zero outside).  Used where the contraction index
 // is the row index of a stored block (left-multiplication of a block by a small matrix).
-template <int VEC, class FA>
+template <int VEC, class FA, class SM>
 __device__ __forceinline__ void tile_gemm_kmajorB(Acc& acc, int K, FA fa, const double* bbase, long long ldb,
-                                                  int ncols, GemmSmem& sm, const double* dummy) {
+                                                  int ncols, SM& sm, const double* dummy) {
   __syncthreads();
   if (threadIdx.x < TB) sm.row_a[0][threadIdx.x] = fa((int)threadIdx.x);
   __syncthreads();
@@ -365,8 +371,8 @@ __device__ __forceinline__ void tile_gemm_kmajorB(Acc& acc, int K, FA fa, const 
 // out += Areg * B^T where Areg is a 64 x 64 tile held in accumulator layout (columns >= K must be zero
 // or K a multiple of 4 covering them) and K <= 64.  B_GLOBAL: fb(rr) -> row pointer, streamed through the
 // cp.async stages; else fb(rr, k) -> element of a shared-memory resident operand.
-template <int VEC, bool B_GLOBAL, class FB>
-__device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB fb, GemmSmem& sm,
+template <int VEC, bool B_GLOBAL, class FB, class SM>
+__device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB fb, SM& sm,
                                                const double* dummy, int mrows = TB, int ncols = TB) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;

@@ -27,7 +27,13 @@ COLS = [
 ]
 
 
-def main(path):
+FAMILY = {"k_prior_tiles": "prior_tiles", "k_predict_fused": "predict_fused", "k_assemble_A": "assemble_A",
+          "k_leaf_solve": "leaf_solve", "k_leaf_gram": "leaf_gram", "k_leaf_factor": "leaf_chol", "k_fold": "fold",
+          "k_knot_factor": "knot_factor", "k_node_factor": "node_factor"}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def main(path, traffic_json=None):
     rows = list(csv.reader(open(path)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -35,7 +41,26 @@ def main(path):
     w.writerow([n + ("[%s]" % units[idx[c]] if c in idx and units[idx[c]] else "") for c, n in COLS])
     for d in data:
         w.writerow([d[idx[c]] if c in idx else "" for c, _ in COLS])
+    if traffic_json:
+        # DRAM bytes (read + write) per kernel family over the captured launches of ONE step, for bench.py's
+        # roofline.traffic (per launch = total / launches)
+        import json
+        fam = {}
+        for d in data:
+            name = d[idx["Kernel Name"]]
+            key = next((v for k, v in FAMILY.items() if k in name), None)
+            if key is None:
+                continue
+            if key == "leaf_gram" and fam.get("leaf_gram", {}).get("launches", 0) >= 1:
+                key = "leaf_gram_T"
+            if key == "leaf_solve" and fam.get("leaf_solve", {}).get("launches", 0) >= 1:
+                key = "leaf_solve_Q"
+            b = sum(float(d[idx[c]]) * UNIT.get(units[idx[c]], 1.0) for c in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            e = fam.setdefault(key, {"dram_bytes": 0.0, "launches": 0})
+            e["dram_bytes"] += b
+            e["launches"] += 1
+        json.dump(fam, open(traffic_json, "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)

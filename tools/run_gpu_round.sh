@@ -2,7 +2,7 @@
 # Usage (from the repo root on the GPU box): bash tools/run_gpu_round.sh [tag] [full-capture kernel regex]
 # gpurun copies back at most 64 MiB: reports are exported to CSV on the box and big .ncu-rep files dropped.
 TAG=${1:-r01}
-KREGEX=${2:-k_predict_fused|k_prior_tiles|k_leaf_gram|k_assemble_A|k_leaf_solve}
+KREGEX=${2:-k_}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo pytest_exit=$?
 tail -3 gpurun_out/pytest_gpu_$TAG.log
@@ -15,7 +15,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 echo ncu1_exit=$?
 python tools/profile_step.py --workload cfg5 > gpurun_out/prof_plain2_cfg5_$TAG.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k "regex:$KREGEX" -c 20 -o gpurun_out/prof_cfg5_$TAG -f python tools/profile_step.py --workload cfg5 > gpurun_out/ncu2_$TAG.log 2>&1
+  -k "regex:$KREGEX" -c 64 -o gpurun_out/prof_cfg5_$TAG -f python tools/profile_step.py --workload cfg5 > gpurun_out/ncu2_$TAG.log 2>&1
 echo ncu2_exit=$?
 if [ -f gpurun_out/prof_cfg5_$TAG.ncu-rep ]; then
   ncu -i gpurun_out/prof_cfg5_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_cfg5_${TAG}_raw.csv 2>/dev/null
