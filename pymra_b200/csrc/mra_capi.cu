@@ -168,11 +168,11 @@ DevCtx make_ctx(mra_handle* h) {
 constexpr size_t GS = sizeof(GemmSmem);     // kernels with segmented products
 constexpr size_t GS1 = sizeof(GemmSmem1);   // single-segment kernels
 size_t smem_knot(int r) { return GS1 + sizeof(double) * ((size_t)r * (r + 1) + 3 * r + NT * 9) + sizeof(int) * r + 16; }
-size_t smem_prior(int r) { return GS + sizeof(double) * ((size_t)2 * r + 2 * TB) + sizeof(int) * TB; }
+size_t smem_prior(int r) { return sizeof(GemmSmemT<2>) + sizeof(double) * ((size_t)2 * r + 2 * TB) + sizeof(int) * TB; }
 size_t smem_gram() { return GS1 + sizeof(int) * 2 * TB; }
 size_t smem_chol(int max_obs) { return GS1 + sizeof(double) * ((size_t)TB * LDB + TB + NT * 9 + TB + ((max_obs + TB - 1) / TB) * TB); }
 size_t smem_solve() { return GS1; }
-size_t smem_plain() { return GS; }
+size_t smem_plain() { return sizeof(GemmSmemT<4>); }   // k_assemble_A: up to 4 children per product
 size_t smem_factor(int r) { return GS1 + sizeof(double) * ((size_t)r * (r + 1) + r + NT * 9); }
 size_t smem_predict(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;

@@ -34,6 +34,7 @@ constexpr int MAXSEG = 8;     // K segments per tile_gemm_seg call
 // only use single-segment products take GemmSmemT<1> (49 KB -> 4 CTAs/SM), the segmented ones GemmSmemT<MAXSEG>.
 template <int NS>
 struct alignas(16) GemmSmemT {
+  static constexpr int NSEG = NS;
   double a[NSTAGE][TB * KC];
   double b[NSTAGE][TB * KC];
   const double* row_a[NS][TB];
@@ -210,8 +211,8 @@ struct NoGen {
   __device__ double operator()(int, int) const { return 0.0; }
 };
 
-template <int VEC, bool GEN = false, class FA, class FB, class FK, class FG = NoGen>
-__device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, FK fk, GemmSmem& sm,
+template <int VEC, bool GEN = false, bool CACHE_PTRS = true, class FA, class FB, class FK, class SM, class FG = NoGen>
+__device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, FK fk, SM& sm,
                                               const double* dummy, int mrows = TB, int ncols = TB, FG fg = FG()) {
   __syncthreads();
   for (int s = 0; s < nseg; ++s) {
@@ -238,7 +239,7 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
     if (lseg < nseg) {
       const int K = sm.seg_k[lseg];
       const bool gen = GEN && lseg == nseg - 1;
-      if (VEC == 2) {
+      if (VEC == 2 && CACHE_PTRS) {
         const int kc = (threadIdx.x & 7) * 2, rb = threadIdx.x >> 3;
         if (cached != lseg) {
           cached = lseg;
