@@ -21,8 +21,26 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace {
+
+#if defined(__x86_64__)
+// lane permutation that packs the lanes selected by an 8-bit mask to the high end, first selected lane last
+struct alignas(32) PackLut {
+  uint32_t idx[256][8];
+  PackLut() {
+    for (int m = 0; m < 256; ++m) {
+      int k = 0;
+      for (int b = 0; b < 8; ++b) idx[m][b] = 0;
+      for (int b = 0; b < 8; ++b)
+        if ((m >> b) & 1) idx[m][7 - k++] = (uint32_t)b;
+    }
+  }
+};
+#endif
 
 // Legacy NumPy MT19937 (mtrand's rk_state): key[624] + pos.  Outputs are produced 624 at a time,
 // already tempered, so the hot loops below read a plain buffer.
@@ -89,7 +107,7 @@ struct MT {
   // jb[i] = interval(i) for i = hi, hi-1, ..., 1 -- the draw sequence of the legacy Fisher-Yates shuffle.
   // Same stream consumption as calling interval() one by one; the rejection loop is branch-free inside a
   // power-of-two segment of i (the mask is constant there): a rejected value is simply overwritten.
-  void shuffle_draws(int32_t* jb, int64_t hi) {
+  void shuffle_draws_scalar(int32_t* jb, int64_t hi) {
     int64_t i = hi;
     while (i >= 1) {
       const uint32_t mask = smear((uint32_t)i);
@@ -106,6 +124,54 @@ struct MT {
         pos += used;
       }
     }
+  }
+#if defined(__x86_64__)
+  // AVX2 version: eight raw outputs per step.  With the running bound i, a masked value v <= i-7 is accepted
+  // whatever happened to the lanes before it and v > i is rejected whatever happened; a group with a value in
+  // between (probability ~7/mask per lane) is replayed by the scalar loop.  Accepted lanes are packed to the
+  // high end in reverse order so that one 32-byte store puts them at jb[i], jb[i-1], ... .
+  __attribute__((target("avx2"))) void shuffle_draws_avx2(int32_t* jb, int64_t hi) {
+    static const PackLut lut;
+    int64_t i = hi;
+    while (i >= 1) {
+      const uint32_t mask = smear((uint32_t)i);
+      const int64_t lo = (int64_t)(mask >> 1) + 1;
+      const __m256i vmask = _mm256_set1_epi32((int)mask);
+      while (i >= lo) {
+        int n = avail();
+        const uint32_t* o = out + pos;
+        int used = 0;
+        while (used + 8 <= n && i >= lo + 8) {
+          const __m256i v = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(o + used)), vmask);
+          const __m256i acc = _mm256_cmpgt_epi32(_mm256_set1_epi32((int)(i - 6)), v);      // v <= i - 7
+          const __m256i rej = _mm256_cmpgt_epi32(v, _mm256_set1_epi32((int)i));            // v > i
+          const int am = _mm256_movemask_ps(_mm256_castsi256_ps(acc));
+          const int rm = _mm256_movemask_ps(_mm256_castsi256_ps(rej));
+          if ((am | rm) != 0xFF) break;
+          const __m256i idx = _mm256_load_si256(reinterpret_cast<const __m256i*>(lut.idx[am]));
+          _mm256_storeu_si256(reinterpret_cast<__m256i*>(jb + i - 7), _mm256_permutevar8x32_epi32(v, idx));
+          i -= __builtin_popcount((unsigned)am);
+          used += 8;
+        }
+        for (int cnt = 0; cnt < 8 && used < n && i >= lo; ++cnt) {
+          const uint32_t v = o[used++] & mask;
+          jb[i] = (int32_t)v;
+          i -= (v <= (uint32_t)i);
+        }
+        pos += used;
+      }
+    }
+  }
+#endif
+  void shuffle_draws(int32_t* jb, int64_t hi) {
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && hi >= 64) {
+      shuffle_draws_avx2(jb, hi);
+      return;
+    }
+#endif
+    shuffle_draws_scalar(jb, hi);
   }
 };
 
