@@ -76,7 +76,8 @@ class _Root(object):
 
     @property
     def var(self):
-        return self._tree._moments()[1]
+        sd = self._tree._moments()[1]          # root.var = sd^2, formed only when somebody asks for it
+        return None if sd is None else sd * sd
 
 
 class MRATree(object):
@@ -140,9 +141,9 @@ class MRATree(object):
             t0 = time.perf_counter()
             mean, sd = self._session.predict()
             if mean is None:            # sharded run with gather="root" on a non-root rank
-                self._mom = (None, None, None)
+                self._mom = (None, None)
             else:
-                self._mom = (np.matrix(mean.reshape(-1, 1)), sd * sd, sd)
+                self._mom = (np.matrix(mean.reshape(-1, 1)), sd)
             self.timings["predict"] = time.perf_counter() - t0
         return self._mom
 
@@ -156,7 +157,7 @@ class MRATree(object):
 
     def predict(self):
         """(root.mean as (N,1) np.matrix, sqrt(root.var) as (N,) ndarray) (MRATree.py:90-94)."""
-        mean, _, sd = self._moments()
+        mean, sd = self._moments()
         return mean, sd
 
     # ---- beyond the reference: frozen-structure re-evaluation for MLE loops (SURVEY.md 8f.1)

@@ -201,8 +201,8 @@ cudaError_t configure_vec(int r, int max_obs) {
   SET_(k_prior_tiles<V_>, smem_prior(r));
   SET_(k_leaf_gram<V_>, smem_gram());
   SET_(k_leaf_factor<V_>, smem_chol(max_obs));
-  SET_((k_leaf_solve<V_, 0>), smem_solve());
-  SET_((k_leaf_solve<V_, 1>), smem_solve());
+  SET_(k_leaf_solve_ut<V_>, smem_solve());
+  SET_(k_leaf_solve_qt<V_>, smem_solve());
   SET_(k_assemble_A<V_>, smem_plain());
   SET_(k_node_factor<V_>, smem_factor(r));
   SET_(k_predict_fused<V_>, smem_predict(r));
@@ -333,7 +333,7 @@ int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary)
     MRA_FOR_VEC(h, LAUNCH("leaf_gram", k_leaf_gram<V_><<<(unsigned)nleaf * nt1, NT, smem_gram(), st>>>(c, leaf_list, 0, nleaf)));
     MRA_FOR_VEC(h, LAUNCH("leaf_chol", k_leaf_factor<V_><<<nleaf, NT, smem_chol(h->max_leaf_obs), st>>>(c, leaf_list)));
     const int nt3 = std::max(1, (h->max_leaf_W - 1 + TB - 1) / TB);
-    MRA_FOR_VEC(h, LAUNCH("leaf_solve", (k_leaf_solve<V_, 0>)<<<(unsigned)nleaf * nt3, NT, smem_solve(), st>>>(c, leaf_list, nt3)));
+    MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve_ut<V_><<<(unsigned)nleaf * nt3, NT, smem_solve(), st>>>(c, leaf_list, nt3)));
   }
   // ---- upward, levels >= shard level
   for (int m = (int)h->internal_at.size() - 1; m >= h->shard_level; --m) {
@@ -389,7 +389,7 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
       const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
       MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<(unsigned)nleaf * nbr * nbo, NT, smem_gram(), st>>>(
                                                c, leaf_list, 1, nleaf)));
-      MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", (k_leaf_solve<V_, 1>)<<<(unsigned)nleaf * nbr, NT, smem_solve(), st>>>(
+      MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", k_leaf_solve_qt<V_><<<(unsigned)nleaf * nbr, NT, smem_solve(), st>>>(
                                                 c, leaf_list, nbr)));
     }
     if (!h->fold_items.empty())

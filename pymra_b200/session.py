@@ -20,20 +20,6 @@ def _dptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-_STAGING = {}
-
-
-def _pinned_staging(n_doubles):
-    """One page-locked staging buffer per process, grown on demand (page-locking 64 MB costs ~15 ms, far more
-    than the copy it speeds up, so it is done once and results are copied out of it)."""
-    import torch
-    t = _STAGING.get("buf")
-    if t is None or t.numel() < n_doubles:
-        t = torch.empty(int(n_doubles), dtype=torch.float64, pin_memory=True)
-        _STAGING["buf"] = t
-    return t
-
-
 class DeviceSession(object):
     def __init__(self, structure, locs, obs, want_predict=True, device=None, group=None, emulate=None,
                  gather="all"):
@@ -167,15 +153,18 @@ class DeviceSession(object):
             self.fetch_likelihood()                           # surfaces a non-SPD status like the plain path
             if self.gather == "root" and self.rank != 0:
                 return None, None
-            host = _pinned_staging(2 * self.N)[:2 * self.N].view(2, self.N)
+            host = torch.empty(2, self.N, dtype=torch.float64, pin_memory=True)
             host.copy_(out)
-            res = host.numpy().copy()
+            res = host.numpy()
             return res[0], res[1]
-        # device -> page-locked staging at PCIe rate, then one host copy into arrays the caller owns
-        stage = _pinned_staging(2 * self.N).numpy()[:2 * self.N].reshape(2, self.N)
-        self.check(self.lib.mra_run_predict(self.h, self.stream(), _dptr(stage[0]), _dptr(stage[1])))
-        res = stage.copy()
-        return res[0], res[1]
+        # page-locked result buffer from torch's caching host allocator: the device->host copy runs at PCIe
+        # rate and the returned arrays are zero-copy views of it (the block is recycled once they are dropped;
+        # an extra host copy out of a shared staging buffer was measured slower)
+        import torch
+        out = torch.empty(2, self.N, dtype=torch.float64, pin_memory=True)
+        host = out.numpy()
+        self.check(self.lib.mra_run_predict(self.h, self.stream(), _dptr(host[0]), _dptr(host[1])))
+        return host[0], host[1]
 
     def predict_dev(self, mean_t=None, sd_t=None, reduce=False):
         """Results into device tensors (caller's order).  Sharded: each rank fills its own rows and zeros
