@@ -29,7 +29,7 @@ struct Arena {
 };
 
 struct Layout {
-  size_t nodes, knot_rows, obs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
+  size_t nodes, knot_rows, obs_rows, unobs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
       mean, var, vnorm, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks, ltiles, GTF, UTF, fold, VKL;
   size_t total;
 };
@@ -64,8 +64,8 @@ struct mra_handle {
   int slot_base = 0, n_slots = 0;
   size_t sroots_off = 0;
   std::vector<NodeDev> nodes;
-  std::vector<int> obs_rows;
-  int max_leaf_obs = 0, max_leaf_rows = 0, max_leaf_W = 1;
+  std::vector<int> obs_rows, unobs_rows;
+  int max_leaf_obs = 0, max_leaf_rows = 0, max_leaf_W = 1, max_leaf_unobs = 0;
   int64_t n_obs_total = 0;
   long long ldv = 0;
   // device
@@ -135,6 +135,8 @@ DevCtx make_ctx(mra_handle* h) {
   c.nodes = at<NodeDev>(h, L.nodes);
   c.knot_rows = at<int>(h, L.knot_rows);
   c.obs_rows = at<int>(h, L.obs_rows);
+  c.unobs_rows = at<int>(h, L.unobs_rows);
+  c.fill_qt = h->want_predict ? 1 : 0;
   c.gather_rows = at<int>(h, L.gather);
   c.xs = at<double>(h, L.xs);
   c.ys = at<double>(h, L.ys);
@@ -387,8 +389,10 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
     const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off);
     if (h->max_leaf_obs > 0) {
       const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
-      MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<(unsigned)nleaf * nbr * nbo, NT, smem_gram(), st>>>(
-                                               c, leaf_list, 1, nleaf)));
+      const int nbu = (h->max_leaf_unobs + TB - 1) / TB;
+      if (nbu > 0)
+        MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<(unsigned)nleaf * nbu * nbo, NT, smem_gram(), st>>>(
+                                                 c, leaf_list, 1, nleaf)));
       MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", k_leaf_solve_qt<V_><<<(unsigned)nleaf * nbr, NT, smem_solve(), st>>>(
                                                 c, leaf_list, nbr)));
     }
@@ -595,9 +599,10 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   h->want_predict = want_predict != 0;
   h->nodes.assign(nn, NodeDev{});
   h->obs_rows.clear();
+  h->unobs_rows.clear();
   long long s_off = 0, di_off = 0, ut_off = 0, qt_off = 0, a_off = 0, gt_off = 0, lp_off = 0, vk_off = 0,
             linv_off = 0;
-  h->max_leaf_obs = h->max_leaf_rows = 0;
+  h->max_leaf_obs = h->max_leaf_rows = h->max_leaf_unobs = 0;
   h->max_leaf_W = 1;
   for (auto& f : h->kflops) f = 0.0;
   for (auto& f : h->kbytes) f = 0.0;
@@ -647,13 +652,17 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       add_work(h, "predict_fused", nr * rr * rr + 2.0 * nr * rr * Kv + 4.0 * nr * rr, 8.0 * nr * rr);
     } else {
       d.obs_off = (int)h->obs_rows.size();
+      d.unobs_off = (int)h->unobs_rows.size();
       if (d.kind == KIND_LEAF) {
         for (int64_t i = 0; i < h->row_count[n]; ++i) {
           const int64_t row = h->row_start[n] + i;
           if (finite_row[row]) h->obs_rows.push_back((int)row);
+          else if (h->want_predict) h->unobs_rows.push_back((int)row);
         }
       }
       d.n_obs = (int)h->obs_rows.size() - d.obs_off;
+      d.n_unobs = (int)h->unobs_rows.size() - d.unobs_off;
+      if (d.n_obs > 0) h->max_leaf_unobs = std::max(h->max_leaf_unobs, d.n_unobs);
       d.ldo = std::max(4, (d.n_obs + 3) / 4 * 4);
       const int nb = (d.n_obs + TB - 1) / TB;
       d.s_off = s_off;
@@ -674,7 +683,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       add_work(h, "assemble_A", W * W * no, 8.0 * no * W);
       if (d.kind == KIND_LEAF) {
         add_work(h, "predict_fused", 2.0 * nl * Kv, 8.0 * nl * (Kv + 2));
-        add_work(h, "leaf_gram_T", 2.0 * nl * no * Kv, 8.0 * ((nl + no) * Kv + nl * no));
+        add_work(h, "leaf_gram_T", 2.0 * (nl - no) * no * Kv, 8.0 * ((nl + no) * Kv + nl * no));
         add_work(h, "leaf_solve_Q", nl * no * no, 8.0 * (2 * nl * no + no * no / 2));
         add_work(h, "predict_fused", 2.0 * nl * no * W + 2.0 * nl * no, 8.0 * (nl * no + no * W));
       }
@@ -712,6 +721,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.nodes = ar.take(sizeof(NodeDev) * nn);
   L.knot_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->knot_rows.size()));
   L.obs_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->obs_rows.size()));
+  L.unobs_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->unobs_rows.size()));
   L.perm = ar.take(sizeof(int) * N);
   L.xs = ar.take(D * N);
   L.ys = ar.take(D * N);
@@ -796,6 +806,9 @@ int mra_upload_data(mra_handle* h, const double* locs, const double* obs, void* 
     CU(cudaMemcpyAsync(h->ws + L.knot_rows, h->knot_rows.data(), sizeof(int) * h->knot_rows.size(), cudaMemcpyHostToDevice, st));
   if (!h->obs_rows.empty())
     CU(cudaMemcpyAsync(h->ws + L.obs_rows, h->obs_rows.data(), sizeof(int) * h->obs_rows.size(), cudaMemcpyHostToDevice, st));
+  if (!h->unobs_rows.empty())
+    CU(cudaMemcpyAsync(h->ws + L.unobs_rows, h->unobs_rows.data(), sizeof(int) * h->unobs_rows.size(),
+                       cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(h->ws + L.perm, h->perm.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
   for (size_t m = 0; m < h->internal_at.size(); ++m) {
     if (!h->internal_at[m].empty())
