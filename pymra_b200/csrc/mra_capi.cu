@@ -598,8 +598,6 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   const int nn = h->n_nodes, r = h->r;
   h->want_predict = want_predict != 0;
   h->nodes.assign(nn, NodeDev{});
-  h->obs_rows.clear();
-  h->unobs_rows.clear();
   long long s_off = 0, di_off = 0, ut_off = 0, qt_off = 0, a_off = 0, gt_off = 0, lp_off = 0, vk_off = 0,
             linv_off = 0;
   h->max_leaf_obs = h->max_leaf_rows = h->max_leaf_unobs = 0;
@@ -614,6 +612,71 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       for (int64_t i = a; i < b; ++i) fr[i] = std::isfinite(obs[pm[i]]) ? 1 : 0;
     });
   }
+  // observed / unobserved row lists of every leaf of this rank: count per leaf, prefix, fill -- all in parallel
+  std::vector<int> leaf_ids, leaf_obs_off, leaf_unobs_off;
+  for (int n = 0; n < nn; ++n)
+    if (h->role[n] && h->kind[n] == KIND_LEAF) leaf_ids.push_back(n);
+  {
+    const int64_t nl = (int64_t)leaf_ids.size();
+    std::vector<int> cnt((size_t)nl, 0);
+    const uint8_t* fr = finite_row.data();
+    const int* lid = leaf_ids.data();
+    int* cp = cnt.data();
+    const int64_t* rs = h->row_start.data();
+    const int64_t* rc = h->row_count.data();
+    auto over_leaves = [&](auto fn) {
+      // parallel_for splits an index range; give it the leaves
+      unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+      if (nl < 1024 || nt == 1) {
+        fn((int64_t)0, nl);
+        return;
+      }
+      std::vector<std::thread> th;
+      const int64_t step = (nl + nt - 1) / nt;
+      for (unsigned t = 0; t < nt; ++t) {
+        const int64_t a = (int64_t)t * step, b = std::min(nl, a + step);
+        if (a < b) th.emplace_back([=] { fn(a, b); });
+      }
+      for (auto& t : th) t.join();
+    };
+    over_leaves([=](int64_t a, int64_t b) {
+      for (int64_t k = a; k < b; ++k) {
+        int c0 = 0;
+        const int64_t s0 = rs[lid[k]], e0 = s0 + rc[lid[k]];
+        for (int64_t row = s0; row < e0; ++row) c0 += fr[row];
+        cp[k] = c0;
+      }
+    });
+    leaf_obs_off.resize((size_t)nl + 1);
+    leaf_unobs_off.resize((size_t)nl + 1);
+    int64_t oo = 0, uo = 0;
+    for (int64_t k = 0; k < nl; ++k) {
+      leaf_obs_off[k] = (int)oo;
+      leaf_unobs_off[k] = (int)uo;
+      oo += cnt[k];
+      if (h->want_predict) uo += (int)rc[lid[k]] - cnt[k];
+    }
+    leaf_obs_off[nl] = (int)oo;
+    leaf_unobs_off[nl] = (int)uo;
+    h->obs_rows.resize((size_t)oo);
+    h->unobs_rows.resize((size_t)uo);
+    int* orow = h->obs_rows.data();
+    int* urow = h->unobs_rows.data();
+    const int* ooff = leaf_obs_off.data();
+    const int* uoff = leaf_unobs_off.data();
+    const bool wp = h->want_predict;
+    over_leaves([=](int64_t a, int64_t b) {
+      for (int64_t k = a; k < b; ++k) {
+        int io = ooff[k], iu = uoff[k];
+        const int64_t s0 = rs[lid[k]], e0 = s0 + rc[lid[k]];
+        for (int64_t row = s0; row < e0; ++row) {
+          if (fr[row]) orow[io++] = (int)row;
+          else if (wp) urow[iu++] = (int)row;
+        }
+      }
+    });
+  }
+  int64_t leaf_cursor = 0;
   for (int n = 0; n < nn; ++n) {
     NodeDev& d = h->nodes[n];
     d.level = h->level[n];
@@ -651,17 +714,16 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       add_work(h, "node_factor", 2.0 * rr * rr * rr / 3.0 + (Kv + 1) * rr * rr, 8.0 * (rr * rr + 2 * (Kv + 1) * rr));
       add_work(h, "predict_fused", nr * rr * rr + 2.0 * nr * rr * Kv + 4.0 * nr * rr, 8.0 * nr * rr);
     } else {
-      d.obs_off = (int)h->obs_rows.size();
-      d.unobs_off = (int)h->unobs_rows.size();
       if (d.kind == KIND_LEAF) {
-        for (int64_t i = 0; i < h->row_count[n]; ++i) {
-          const int64_t row = h->row_start[n] + i;
-          if (finite_row[row]) h->obs_rows.push_back((int)row);
-          else if (h->want_predict) h->unobs_rows.push_back((int)row);
-        }
+        d.obs_off = leaf_obs_off[leaf_cursor];
+        d.unobs_off = leaf_unobs_off[leaf_cursor];
+        d.n_obs = leaf_obs_off[leaf_cursor + 1] - d.obs_off;
+        d.n_unobs = leaf_unobs_off[leaf_cursor + 1] - d.unobs_off;
+        ++leaf_cursor;
+      } else {          // orphan rows: no data, no residual term
+        d.obs_off = d.unobs_off = 0;
+        d.n_obs = d.n_unobs = 0;
       }
-      d.n_obs = (int)h->obs_rows.size() - d.obs_off;
-      d.n_unobs = (int)h->unobs_rows.size() - d.unobs_off;
       if (d.n_obs > 0) h->max_leaf_unobs = std::max(h->max_leaf_unobs, d.n_unobs);
       d.ldo = std::max(4, (d.n_obs + 3) / 4 * 4);
       const int nb = (d.n_obs + TB - 1) / TB;
