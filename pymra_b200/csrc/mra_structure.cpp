@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <atomic>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <cstdint>
 #include <cstdlib>
@@ -408,13 +409,16 @@ struct Builder {
 // inside the child all come from the bit planes, so it never touches the 20 bytes/location row data.
 struct LevelBits {
   std::vector<uint64_t> lo, hi;    // code = 2*[x > mean_x] + [y > mean_y]: hi = x bit, lo = y bit
-  std::vector<int32_t> cum;        // cum[4*b + c] = #positions < 64*b with code c (whole level)
+  std::vector<int32_t> cum;        // cum[4*b + c] = #positions in [base, base + 64*b) with code c
+  int64_t base = 0;                // first position covered (0 for a whole level, the subtree start otherwise)
   inline int code(int64_t x) const {
+    x -= base;
     const int64_t b = x >> 6;
     const int sh = (int)(x & 63);
     return (int)(((hi[b] >> sh) & 1ull) * 2 + ((lo[b] >> sh) & 1ull));
   }
-  inline int64_t rank(int c, int64_t x) const {      // #positions < x with code c
+  inline int64_t rank(int c, int64_t x) const {      // #positions in [base, x) with code c
+    x -= base;
     const int64_t b = x >> 6;
     const uint64_t wl = (c & 1) ? lo[b] : ~lo[b], wh = (c & 2) ? hi[b] : ~hi[b];
     const uint64_t low = (x & 63) ? ((1ull << (x & 63)) - 1ull) : 0ull;
@@ -445,7 +449,10 @@ struct Partitioner {
   int32_t* rows[2];
   double *xs[2], *ys[2];
   uint8_t* code = nullptr;
-  std::vector<LevelBits> lv;
+  std::vector<LevelBits> lv;                 // levels < S: whole-level bit planes
+  int S = 0;                                 // levels >= S are partitioned subtree by subtree (4^S subtrees)
+  std::vector<std::vector<LevelBits>> sub;   // sub[k][L - S]: bit planes of subtree k at level L
+  std::unique_ptr<std::atomic<int>[]> sub_ready;
   std::atomic<int> ready{0};
   std::atomic<int> failed{0};
   struct PNode {
@@ -547,23 +554,26 @@ struct Partitioner {
       if (cnt[c] == 0) failed.store(1);
   }
 
-  void build_bits(int L) {
-    LevelBits& lb = lv[L];
-    const int64_t nblk = (N >> 6) + 2;
+  // bit planes + cumulative block counts of positions [s0, e0) from the code bytes; nt threads
+  void build_bits(LevelBits& lb, int64_t s0, int64_t e0, int nt) {
+    const int64_t n = e0 - s0;
+    const int64_t nblk = (n >> 6) + 2;
+    lb.base = s0;
     lb.lo.assign(nblk, 0);
     lb.hi.assign(nblk, 0);
     lb.cum.assign(nblk * 4, 0);
-    const int nc = nthreads * 2;
+    const int nc = std::max(1, nt * 2);
     const int64_t bstep = (nblk + nc - 1) / nc;
     std::vector<int64_t> cc((size_t)nc * 4, 0);
-    run_parallel(nthreads, nc, [&](int64_t k) {
+    const uint8_t* cd0 = code + s0;
+    run_parallel(nt, nc, [&](int64_t k) {
       const int64_t b0 = k * bstep, b1 = std::min(nblk, b0 + bstep);
       int64_t c4[4] = {0, 0, 0, 0};
       for (int64_t b = b0; b < b1; ++b) {
         uint64_t wl = 0, wh = 0;
-        const int64_t x0 = b << 6, x1 = std::min(N, x0 + 64);
+        const int64_t x0 = b << 6, x1 = std::min(n, x0 + 64);
         for (int64_t x = x0; x < x1; ++x) {
-          const uint64_t cd = code[x];
+          const uint64_t cd = cd0[x];
           wl |= (cd & 1ull) << (x - x0);
           wh |= (cd >> 1) << (x - x0);
         }
@@ -587,7 +597,7 @@ struct Partitioner {
         acc += cc[4 * k + c];
       }
     }
-    run_parallel(nthreads, nc, [&](int64_t k) {
+    run_parallel(nt, nc, [&](int64_t k) {
       const int64_t b0 = k * bstep, b1 = std::min(nblk, b0 + bstep);
       int64_t run[4] = {base[4 * k], base[4 * k + 1], base[4 * k + 2], base[4 * k + 3]};
       for (int64_t b = b0; b < b1; ++b)
@@ -599,9 +609,21 @@ struct Partitioner {
     });
   }
 
+  // levels S .. M-1 of the subtree rooted at `root` (a level-S node), one thread, BFS inside the subtree
+  void run_subtree(int k, const PNode& root) {
+    std::vector<PNode> cur{root}, next;
+    for (int L = S; L < M; ++L) {
+      next.assign(cur.size() * 4, PNode{0, 0, 0.0, 0.0});
+      for (size_t i = 0; i < cur.size(); ++i) do_node(cur[i], &next[4 * i], L & 1);
+      if (failed.load()) return;
+      build_bits(sub[k][L - S], root.s, root.e, 1);
+      cur.swap(next);
+    }
+  }
+
   void run(double sx0, double sy0) {
     std::vector<PNode> cur{PNode{0, N, sx0, sy0}}, next;
-    for (int L = 0; L < M; ++L) {
+    for (int L = 0; L < S; ++L) {
       next.assign(cur.size() * 4, PNode{0, 0, 0.0, 0.0});
       const int b = L & 1;
       // big nodes one after the other (all threads inside), the rest in parallel
@@ -614,13 +636,29 @@ struct Partitioner {
         const int64_t i = small[k];
         do_node(cur[i], &next[4 * i], b);
       });
-      if (failed.load()) {
-        ready.store(M + 1, std::memory_order_release);
-        return;
-      }
-      build_bits(L);
+      if (failed.load()) break;
+      build_bits(lv[L], 0, N, nthreads);
       ready.store(L + 1, std::memory_order_release);
       cur.swap(next);
+    }
+    const int nsub = (int)sub.size();
+    if (!failed.load() && S < M) {
+      // the subtrees below level S are independent: workers take them in DFS order, so the RNG replay (which
+      // visits them in the same order) rarely has to wait
+      std::atomic<int> nextk{0};
+      std::vector<std::thread> th;
+      for (int t = 0; t < std::min(nthreads, nsub); ++t)
+        th.emplace_back([&] {
+          for (int k; (k = nextk.fetch_add(1)) < nsub;) {
+            if (!failed.load()) run_subtree(k, cur[k]);
+            sub_ready[k].store(1, std::memory_order_release);
+          }
+        });
+      for (auto& t : th) t.join();
+    }
+    if (failed.load()) {
+      ready.store(M + 1, std::memory_order_release);
+      for (int k = 0; k < nsub; ++k) sub_ready[k].store(1, std::memory_order_release);
     }
   }
 };
@@ -630,7 +668,8 @@ struct RankBuilder {
   Partitioner* P;
   int M;
 
-  void visit(int parent, int level, int64_t s, int64_t e, int levels_left, const std::vector<KEnt>& kp) {
+  // idx: index of the node inside its level (regular 4-ary tree), which also names its level-S subtree
+  void visit(int parent, int level, int64_t idx, int64_t s, int64_t e, int levels_left, const std::vector<KEnt>& kp) {
     Builder& b = *B;
     if (b.status) return;
     const int me = (int)b.rec.size();
@@ -673,12 +712,20 @@ struct RankBuilder {
       }
       for (; j < kp.size(); ++j) mk.push_back(kp[j]);
     }
-    while (P->ready.load(std::memory_order_acquire) <= level) std::this_thread::yield();
+    const LevelBits* lbp;
+    if (level < P->S) {
+      while (P->ready.load(std::memory_order_acquire) <= level) std::this_thread::yield();
+      lbp = &P->lv[level];
+    } else {
+      const int64_t k = idx >> (2 * (level - P->S));            // ancestor at level S
+      while (!P->sub_ready[k].load(std::memory_order_acquire)) std::this_thread::yield();
+      lbp = &P->sub[k][level - P->S];
+    }
     if (P->failed.load()) {
       b.status = 1;
       return;
     }
-    const LevelBits& lb = P->lv[level];
+    const LevelBits& lb = *lbp;
     int64_t base[4], cnt[4], off[4];
     for (int c = 0; c < 4; ++c) {
       base[c] = lb.rank(c, s);
@@ -703,7 +750,7 @@ struct RankBuilder {
     for (int c = 0; c < 4; ++c) {
       if (fork) b.rng = saved;
       if (c == 0) b.rec[me].first_child = (int)b.rec.size();
-      visit(me, level + 1, off[c], off[c] + cnt[c], levels_left - 1, ckp[c]);
+      visit(me, level + 1, 4 * idx + c, off[c], off[c] + cnt[c], levels_left - 1, ckp[c]);
       if (b.status) return;
     }
     if (fork) b.rng = saved;
@@ -774,10 +821,17 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
       P.ys[b] = B.ys[b];
     }
     P.code = B.code;
-    P.lv.resize(M);
+    P.S = std::min(2, (int)M);
+    P.lv.resize(P.S);
+    {
+      const int nsub = P.S < M ? 1 << (2 * P.S) : 0;
+      P.sub.assign(nsub, std::vector<LevelBits>(M - P.S));
+      P.sub_ready.reset(new std::atomic<int>[std::max(1, nsub)]);
+      for (int k = 0; k < nsub; ++k) P.sub_ready[k].store(0);
+    }
     std::thread worker([&] { P.run(sx, sy); });
     RankBuilder RB{&B, &P, M};
-    RB.visit(-1, 0, 0, N, M, std::vector<KEnt>());
+    RB.visit(-1, 0, 0, 0, N, M, std::vector<KEnt>());
     worker.join();
     if (!B.status && !P.failed.load()) {
       std::memcpy(B.perm, B.rows[M & 1], sizeof(int32_t) * N);
