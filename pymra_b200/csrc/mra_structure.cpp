@@ -220,11 +220,36 @@ struct Builder {
   int32_t *scratch, *draws, *perm;
   uint8_t *code, *slot_of;
   uint64_t* bits;                        // tracked-position bitmap of the reverse selection (all zero between nodes)
-  static constexpr int64_t REVERSE_MIN = 32768;
+  static constexpr int64_t REVERSE_MIN = 512;
   std::vector<Rec> rec;
   std::vector<int32_t> knot_tree_row;    // r per internal node, in reference knot order; resolved at the leaves
   std::vector<int32_t> kinds_local;      // r per internal node
   int status = 0;
+
+#if defined(__x86_64__)
+  // Tests eight draws at a time against the tracked-position bitmap (two 4-wide 64-bit gathers); a group with
+  // a hit -- rare: about r ln(n/r) of n draws -- is replayed in order by the scalar step, which may change
+  // the bitmap.  Returns the first index it did not process.
+  template <class F>
+  __attribute__((target("avx2"))) int64_t undo_scan_avx2(const int32_t* jb, int64_t from, int64_t n, F step) {
+    int64_t i = from;
+    const long long* b64 = reinterpret_cast<const long long*>(bits);
+    const __m256i one = _mm256_set1_epi64x(1), m63 = _mm256_set1_epi64x(63);
+    for (; i + 8 <= n; i += 8) {
+      const __m128i j0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(jb + i));
+      const __m128i j1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(jb + i + 4));
+      const __m256i w0 = _mm256_i32gather_epi64(b64, _mm_srli_epi32(j0, 6), 8);
+      const __m256i w1 = _mm256_i32gather_epi64(b64, _mm_srli_epi32(j1, 6), 8);
+      const __m256i s0 = _mm256_and_si256(_mm256_cvtepu32_epi64(j0), m63);
+      const __m256i s1 = _mm256_and_si256(_mm256_cvtepu32_epi64(j1), m63);
+      const __m256i h0 = _mm256_and_si256(_mm256_srlv_epi64(w0, s0), one);
+      const __m256i h1 = _mm256_and_si256(_mm256_srlv_epi64(w1, s1), one);
+      if (!_mm256_testz_si256(_mm256_or_si256(h0, h1), one))
+        for (int k = 0; k < 8; ++k) step(i + k);
+    }
+    return i;
+  }
+#endif
 
   // a[0..r) of np.random.permutation(n) on the legacy stream (== np.random.choice(arange(n), r, False))
   void first_r_of_permutation(int64_t n, int32_t* out) {
@@ -256,17 +281,23 @@ struct Builder {
       bits[p >> 6] |= 1ull << (p & 63);
       slot_of[p] = (uint8_t)p;
     }
-    for (int64_t i = r; i < n; ++i) {
+    auto undo_step = [&](int64_t i) {
       const int32_t j = jb[i];
       if ((bits[j >> 6] >> (j & 63)) & 1ull) {
-        if (j == i) continue;
+        if (j == i) return;
         const uint8_t sl = slot_of[j];
         bits[j >> 6] &= ~(1ull << (j & 63));
         bits[i >> 6] |= 1ull << (i & 63);
         slot_of[i] = sl;
         key[sl] = (int32_t)i;
       }
-    }
+    };
+    int64_t i0 = r;
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) i0 = undo_scan_avx2(jb, r, n, undo_step);
+#endif
+    for (int64_t i = i0; i < n; ++i) undo_step(i);
     for (int p = 0; p < r; ++p) {
       out[p] = key[p];                                 // initial array is arange: value == position
       bits[key[p] >> 6] &= ~(1ull << (key[p] & 63));
