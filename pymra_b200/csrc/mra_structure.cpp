@@ -220,7 +220,8 @@ struct Builder {
   int32_t *scratch, *draws, *perm;
   uint8_t *code, *slot_of;
   uint64_t* bits;                        // tracked-position bitmap of the reverse selection (all zero between nodes)
-  static constexpr int64_t REVERSE_MIN = 512;
+  static constexpr int64_t REVERSE_MAXBUF = 32768;   // size of the small-node draw buffer
+  int64_t REVERSE_MIN = 16384;                        // nodes below this run the plain shuffle (MRA_REVERSE_MIN overrides)
   std::vector<Rec> rec;
   std::vector<int32_t> knot_tree_row;    // r per internal node, in reference knot order; resolved at the leaves
   std::vector<int32_t> kinds_local;      // r per internal node
@@ -816,7 +817,8 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
     B.ys[b] = pool.ys[b].get(N);
   }
   B.scratch = pool.scratch.get(N);
-  B.draws = pool.draws.get(std::min<int64_t>(N, Builder::REVERSE_MIN) + 1);
+  if (const char* e = std::getenv("MRA_REVERSE_MIN")) B.REVERSE_MIN = std::max<int64_t>(64, std::min<int64_t>(Builder::REVERSE_MAXBUF, std::atoll(e)));
+  B.draws = pool.draws.get(std::min<int64_t>(N, Builder::REVERSE_MAXBUF) + 1);
   B.perm = pool.perm.get(N);
   B.code = pool.code.get(N);
   B.slot_of = pool.slot_of.get(N);
@@ -831,14 +833,18 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
       !B.perm || !B.code || !B.slot_of || !B.bits)
     return MRA_ERR_NOMEM;
   double sx = 0.0, sy = 0.0;
-  for (int64_t i = 0; i < N; ++i) {
-    B.rows[0][i] = (int32_t)i;
-    const double x = locs[2 * i], y = locs[2 * i + 1];
-    B.xs[0][i] = x;
-    B.ys[0][i] = y;
-    sx += x;
-    sy += y;
-  }
+  // level-0 arrays and the root's column sums (sequential, np.mean's order)
+  auto init_level0 = [&] {
+    sx = sy = 0.0;
+    for (int64_t i = 0; i < N; ++i) {
+      B.rows[0][i] = (int32_t)i;
+      const double x = locs[2 * i], y = locs[2 * i + 1];
+      B.xs[0][i] = x;
+      B.ys[0][i] = y;
+      sx += x;
+      sy += y;
+    }
+  };
   bool done = false;
   if (M >= 1 && N >= (int64_t)1 << 16) {
     // threaded two-phase build; falls back to the serial DFS below when the tree is not regular
@@ -860,7 +866,10 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
       P.sub_ready.reset(new std::atomic<int>[std::max(1, nsub)]);
       for (int k = 0; k < nsub; ++k) P.sub_ready[k].store(0);
     }
-    std::thread worker([&] { P.run(sx, sy); });
+    std::thread worker([&] {     // the root's draws need nothing but N: the RNG replay starts right away
+      init_level0();
+      P.run(sx, sy);
+    });
     RankBuilder RB{&B, &P, M};
     RB.visit(-1, 0, 0, 0, N, M, std::vector<KEnt>());
     worker.join();
@@ -876,12 +885,10 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
       std::memcpy(B.rng.key, mt_key, sizeof(uint32_t) * 624);
       B.rng.pos = *mt_pos;
       B.rng.out_valid = false;
-      for (int64_t i = 0; i < N; ++i) {
-        B.rows[0][i] = (int32_t)i;
-        B.xs[0][i] = locs[2 * i];
-        B.ys[0][i] = locs[2 * i + 1];
-      }
+      init_level0();
     }
+  } else {
+    init_level0();
   }
   if (!done) B.visit(-1, 0, 0, N, 0, M, std::vector<KEnt>(), sx, sy);
   if (B.status) return MRA_BUILD_UNSUPPORTED;
