@@ -36,7 +36,9 @@ enum mra_status {
 
 enum mra_cov_family {      /* pyMRA/MRATools.py */
   MRA_COV_EXP = 0,         /* ExpCovFun  :265-269   exp(-D/l)                          */
-  MRA_COV_MATERN32 = 1     /* Matern32   :289-293   sig*(1+sqrt(3)D/l)*exp(-sqrt(3)D/l) */
+  MRA_COV_MATERN32 = 1,    /* Matern32   :289-293   sig*(1+sqrt(3)D/l)*exp(-sqrt(3)D/l) */
+  MRA_COV_MATERN52 = 2,    /* Matern52   :281-285   sig*(1+sqrt(5)D/l+5D^2/(3l^2))*exp(-sqrt(5)D/l) */
+  MRA_COV_GAUSSIAN = 3     /* GaussianCovFun :297-301  sig*exp(-D^2/(2 l^2)) */
 };
 
 enum mra_node_kind { MRA_NODE_INTERNAL = 0, MRA_NODE_LEAF = 1, MRA_NODE_ORPHAN = 2 };

@@ -90,6 +90,10 @@ def make_cov(family, l, sig):
         return lambda a, b: mt.ExpCovFun(a, b, l=l)
     if family == "matern32":
         return lambda a, b: mt.Matern32(a, b, l=l, sig=sig)
+    if family == "matern52":
+        return lambda a, b: mt.Matern52(a, b, l=l, sig=sig)
+    if family == "gaussian":
+        return lambda a, b: mt.GaussianCovFun(a, b, l=l, sig=sig)
     raise ValueError(family)
 
 
@@ -221,6 +225,20 @@ def ka4_large_crit0():
 def g48_m32():
     locs, obs = grid_case(48, 48, 0.4, 1)
     run_case("g48_m32", locs, obs, 8, 1e-2, "matern32", 0.3, 1.0, M=2, seed=5)
+
+
+@case
+def g48_m52():
+    locs, obs = grid_case(48, 48, 0.4, 11)
+    run_case("g48_m52", locs, obs, 6, 2e-2, "matern52", 0.08, 1.5, M=2, seed=5,
+             note="Matern52 (MRATools.py:281-285), SURVEY 8f.3")
+
+
+@case
+def g48_gauss():
+    locs, obs = grid_case(48, 48, 0.5, 12)
+    run_case("g48_gauss", locs, obs, 4, 5e-2, "gaussian", 0.03, 1.0, M=2, seed=5,
+             note="GaussianCovFun (MRATools.py:297-301), SURVEY 8f.3")
 
 
 @case

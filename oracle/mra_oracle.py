@@ -59,11 +59,27 @@ def matern32_cov(a, b, l=1.0, sig=1.0):
     return sig * np.multiply(1 + np.sqrt(3) * D / l, np.exp(-np.sqrt(3) * D / l))
 
 
+def matern52_cov(a, b, l=1.0, sig=1.0):
+    """sig*(1+sqrt(5)D/l+(5/3)(D/l)^2)*exp(-sqrt(5)D/l) (MRATools.py:281-285)."""
+    D = cdist(_as2d(a), _as2d(b))
+    return sig * np.multiply(1 + np.sqrt(5) * D / l + (5 / 3) * np.square(D / l), np.exp(-np.sqrt(5) * D / l))
+
+
+def gaussian_cov(a, b, l=1.0, sig=1.0):
+    """sig*exp(-D^2/(2 l^2)) (MRATools.py:297-301)."""
+    D = cdist(_as2d(a), _as2d(b))
+    return sig * np.exp(-np.square(D) / (2 * (l ** 2)))
+
+
 def make_cov(family, l, sig=1.0):
     if family == "exp":
         return lambda a, b: exp_cov(a, b, l)
     if family == "matern32":
         return lambda a, b: matern32_cov(a, b, l, sig)
+    if family == "matern52":
+        return lambda a, b: matern52_cov(a, b, l, sig)
+    if family == "gaussian":
+        return lambda a, b: gaussian_cov(a, b, l, sig)
     raise ValueError("unknown covariance family %r" % (family,))
 
 

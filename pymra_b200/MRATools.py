@@ -48,3 +48,15 @@ def Matern32(locs, locs2=np.array([]), l=1, sig=1, circular=False):
     """sig*(1+sqrt(3)D/l)*exp(-sqrt(3)D/l) (MRATools.py:289-293)."""
     D = dist(locs, locs2, circular)
     return np.matrix(sig * np.multiply(1 + np.sqrt(3) * D / l, np.exp(-np.sqrt(3) * D / l)))
+
+
+def Matern52(locs, locs2=np.array([]), l=1, sig=1, circular=False):
+    """sig*(1+sqrt(5)D/l+(5/3)(D/l)^2)*exp(-sqrt(5)D/l) (MRATools.py:281-285)."""
+    D = dist(locs, locs2, circular)
+    return np.matrix(sig * np.multiply(1 + np.sqrt(5) * D / l + (5 / 3) * np.square(D / l), np.exp(-np.sqrt(5) * D / l)))
+
+
+def GaussianCovFun(locs, locs2=np.array([]), l=1, sig=1, circular=False):
+    """sig*exp(-D^2/(2 l^2)) (MRATools.py:297-301)."""
+    D = dist(locs, locs2, circular)
+    return np.matrix(sig * np.exp(-np.square(D) / (2 * (l ** 2))))

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpymra_b200.so")
 MRA_OK = 0
 STATUS_NAMES = {0: "MRA_OK", -1: "MRA_ERR_ARG", -2: "MRA_ERR_CUDA", -3: "MRA_ERR_STATE",
                 -4: "MRA_ERR_NOT_SPD", -5: "MRA_ERR_NOMEM"}
-COV_EXP, COV_MATERN32 = 0, 1
+COV_EXP, COV_MATERN32, COV_MATERN52, COV_GAUSSIAN = 0, 1, 2, 3
 
 _p32 = C.POINTER(C.c_int32)
 _p64 = C.POINTER(C.c_int64)

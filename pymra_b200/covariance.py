@@ -10,9 +10,11 @@ import math
 
 import numpy as np
 
-from ._ffi import COV_EXP, COV_MATERN32
+from ._ffi import COV_EXP, COV_GAUSSIAN, COV_MATERN32, COV_MATERN52
 
 _S3 = math.sqrt(3.0)
+_S5 = math.sqrt(5.0)
+_NAMES = {COV_EXP: "exp", COV_MATERN32: "matern32", COV_MATERN52: "matern52", COV_GAUSSIAN: "gaussian"}
 
 
 class CovDescriptor(object):
@@ -23,12 +25,17 @@ class CovDescriptor(object):
 
     @property
     def name(self):
-        return "exp" if self.family == COV_EXP else "matern32"
+        return _NAMES[self.family]
 
     def __call__(self, D):
         D = np.asarray(D, dtype=np.float64)
         if self.family == COV_EXP:
             return self.sig * np.exp(-D / self.l)
+        if self.family == COV_GAUSSIAN:
+            return self.sig * np.exp(-np.square(D) / (2 * self.l ** 2))
+        if self.family == COV_MATERN52:
+            t = _S5 * D / self.l
+            return self.sig * ((1 + t + (5.0 / 3.0) * np.square(D / self.l)) * np.exp(-t))
         t = _S3 * D / self.l
         return self.sig * ((1 + t) * np.exp(-t))
 
@@ -43,22 +50,19 @@ def _eval(cov, a, b):
     return out
 
 
-def _solve_matern_t(g):
-    """t > 0 with (1+t)exp(-t) = g, 0 < g < 1."""
+def _solve_matern_t(g, order=3):
+    """t > 0 with p(t) exp(-t) = g, 0 < g < 1; p = 1+t (Matern 3/2) or 1+t+t^2/3 (Matern 5/2)."""
+    poly = (lambda t: 1 + t) if order == 3 else (lambda t: 1 + t + t * t / 3.0)
     lo, hi = 0.0, 1.0
-    while (1 + hi) * math.exp(-hi) > g:
+    while poly(hi) * math.exp(-hi) > g:
         hi *= 2.0
     for _ in range(200):
         mid = 0.5 * (lo + hi)
-        if (1 + mid) * math.exp(-mid) > g:
+        if poly(mid) * math.exp(-mid) > g:
             lo = mid
         else:
             hi = mid
-    t = 0.5 * (lo + hi)
-    for _ in range(4):       # Newton polish
-        f = (1 + t) * math.exp(-t) - g
-        t -= f / (-t * math.exp(-t))
-    return t
+    return 0.5 * (lo + hi)
 
 
 def introspect(cov, d, rtol=1e-12, n_check=192, seed=12345):
@@ -85,7 +89,9 @@ def introspect(cov, d, rtol=1e-12, n_check=192, seed=12345):
         raise ValueError("could not probe the covariance closure (no distance with 0 < c(d)/c(0) < 1)")
     k = ok[len(ok) // 2]
     cands = [CovDescriptor(COV_EXP, -dists[k] / math.log(g[k]), c0),
-             CovDescriptor(COV_MATERN32, _S3 * dists[k] / _solve_matern_t(g[k]), c0)]
+             CovDescriptor(COV_MATERN32, _S3 * dists[k] / _solve_matern_t(g[k], 3), c0),
+             CovDescriptor(COV_MATERN52, _S5 * dists[k] / _solve_matern_t(g[k], 5), c0),
+             CovDescriptor(COV_GAUSSIAN, dists[k] / math.sqrt(-2.0 * math.log(g[k])), c0)]
     rng = np.random.RandomState(seed)
     a = rng.uniform(0, 1, size=(n_check, d))
     b = rng.uniform(0, 1, size=(n_check, d)) * rng.choice([1e-3, 1e-1, 1.0, 5.0], size=(n_check, 1))
@@ -100,6 +106,6 @@ def introspect(cov, d, rtol=1e-12, n_check=192, seed=12345):
         errs.append(err)
         if err <= rtol:
             return cand
-    raise ValueError("cov is not an ExpCovFun/Matern32 closure (mismatch exp %.2e, matern32 %.2e relative); "
+    raise ValueError("cov is not an ExpCovFun / Matern32 / Matern52 / GaussianCovFun closure (relative mismatch %s); "
                      "other covariance functions are outside the accelerated path and there is no CPU fallback"
-                     % (errs[0], errs[1]))
+                     % ", ".join("%s %.2e" % (c.name, e) for c, e in zip(cands, errs)))

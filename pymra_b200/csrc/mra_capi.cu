@@ -915,13 +915,14 @@ int mra_upload_data(mra_handle* h, const double* locs, const double* obs, void* 
 
 int mra_set_cov(mra_handle* h, int family, double length_scale, double sig) {
   if (!h) return MRA_ERR_ARG;
-  if (family != MRA_COV_EXP && family != MRA_COV_MATERN32) return fail(h, MRA_ERR_ARG, "unknown covariance family");
+  if (family < MRA_COV_EXP || family > MRA_COV_GAUSSIAN) return fail(h, MRA_ERR_ARG, "unknown covariance family");
   if (!(length_scale > 0.0) || !(sig > 0.0)) return fail(h, MRA_ERR_ARG, "length scale and sig must be positive");
   h->cov.family = family;
   h->cov.l = length_scale;
   h->cov.sig = sig;
   h->cov.c0 = h->cov.sig;
-  h->cov.a = (family == MRA_COV_EXP ? 1.0 : 1.7320508075688772) / length_scale;
+  if (family == MRA_COV_GAUSSIAN) h->cov.a = 1.0 / (2.0 * length_scale * length_scale);
+  else h->cov.a = (family == MRA_COV_EXP ? 1.0 : family == MRA_COV_MATERN32 ? 1.7320508075688772 : 2.23606797749979) / length_scale;
   h->cov_set = true;
   h->lik_done = h->pred_done = false;
   return MRA_OK;

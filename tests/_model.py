@@ -29,6 +29,12 @@ def cov_fn(family, l, sig):
     if family == "matern32":
         s3 = np.sqrt(3.0)
         return (lambda a, b: sig * (1 + s3 * cdist(a, b) / l) * np.exp(-s3 * cdist(a, b) / l)), sig
+    if family == "matern52":
+        s5 = np.sqrt(5.0)
+        return (lambda a, b: sig * (1 + s5 * cdist(a, b) / l + (5.0 / 3.0) * np.square(cdist(a, b) / l))
+                * np.exp(-s5 * cdist(a, b) / l)), sig
+    if family == "gaussian":
+        return (lambda a, b: sig * np.exp(-np.square(cdist(a, b)) / (2 * l * l))), sig
     raise ValueError(family)
 
 

@@ -28,8 +28,13 @@ def structure_for(g):
 def make_cov(g):
     import pymra_b200.MRATools as mt
     l, sig = float(g["l"]), float(g["sig"])
-    if str(g["family"]) == "exp":
+    fam = str(g["family"])
+    if fam == "exp":
         return lambda a, b: mt.ExpCovFun(a, b, l=l)
+    if fam == "matern52":
+        return lambda a, b: mt.Matern52(a, b, l=l, sig=sig)
+    if fam == "gaussian":
+        return lambda a, b: mt.GaussianCovFun(a, b, l=l, sig=sig)
     return lambda a, b: mt.Matern32(a, b, l=l, sig=sig)
 
 

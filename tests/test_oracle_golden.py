@@ -9,7 +9,9 @@ from _util import errs, golden_names, golden_structure, load_golden, oracle_for
 # SURVEY.md section 0 finding 9; these bounds are ~3x the measured oracle-vs-reference gaps.
 LOOSE = {"ka4_large_m3": (3e-8, 1e-5, 1e-4), "readme_literal_small": (2e-8, 5e-7, 1e-2),
          "g33x47_m32": (5e-9, 1e-7, 2e-3), "g48_m32": (5e-9, 1e-7, 2e-3), "g64_allobs": (1e-9, 5e-8, 5e-4),
-         "g96_m32_r16": (1e-9, 5e-8, 5e-4), "g125_m32_r16": (1e-9, 5e-8, 1e-4), "m0_dense": (1e-9, 1e-8, 2e-7)}
+         "g96_m32_r16": (1e-9, 5e-8, 5e-4), "g125_m32_r16": (1e-9, 5e-8, 1e-4), "m0_dense": (1e-9, 1e-8, 2e-7),
+         # smooth kernels: the reference's inv()-based recursion is noisier still
+         "g48_m52": (3e-9, 3e-7, 5e-4), "g48_gauss": (1e-8, 5e-7, 1.5e-3)}
 
 
 @pytest.mark.parametrize("name", golden_names())
