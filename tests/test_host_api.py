@@ -44,8 +44,14 @@ def test_cov_introspection(d):
     assert c.name == "exp" and abs(c.l - 2) < 1e-13 and c.sig == 1.0
     c = introspect(lambda a, b: 2.5 * mt.ExpCovFun(a, b, l=0.03), d)
     assert c.name == "exp" and abs(c.l - 0.03) < 1e-15 and abs(c.sig - 2.5) < 1e-14
+    c = introspect(lambda a, b: mt.Matern52(a, b, l=0.2, sig=0.6), d)
+    assert c.name == "matern52" and abs(c.l - 0.2) < 1e-13 and abs(c.sig - 0.6) < 1e-14
+    c = introspect(lambda a, b: mt.GaussianCovFun(a, b, l=0.07, sig=1.3), d)
+    assert c.name == "gaussian" and abs(c.l - 0.07) < 1e-13 and abs(c.sig - 1.3) < 1e-14
+    c = introspect(lambda a, b: np.exp(-np.square(mt.dist(a, b))), d)          # a Gaussian in disguise: 2 l^2 = 1
+    assert c.name == "gaussian" and abs(c.l - np.sqrt(0.5)) < 1e-13
     with pytest.raises(ValueError):
-        introspect(lambda a, b: np.exp(-np.square(mt.dist(a, b))), d)
+        introspect(lambda a, b: 1.0 / (1.0 + np.square(mt.dist(a, b))), d)     # rational quadratic: not supported
     with pytest.raises(NotImplementedError):
         introspect(np.matrix(np.eye(3)), d)
 
