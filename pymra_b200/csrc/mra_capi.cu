@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -99,6 +100,7 @@ namespace {
 template <class F>
 void parallel_for(int64_t n, F fn) {
   unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  if (const char* e = std::getenv("MRA_HOST_THREADS")) nt = (unsigned)std::max(1, std::min((int)nt, std::atoi(e)));
   if (n < (int64_t)1 << 18 || nt == 1) {
     fn((int64_t)0, n);
     return;
@@ -627,6 +629,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
     auto over_leaves = [&](auto fn) {
       // parallel_for splits an index range; give it the leaves
       unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+      if (const char* e = std::getenv("MRA_HOST_THREADS")) nt = (unsigned)std::max(1, std::min((int)nt, std::atoi(e)));
       if (nl < 1024 || nt == 1) {
         fn((int64_t)0, nl);
         return;

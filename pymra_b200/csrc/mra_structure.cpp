@@ -852,6 +852,7 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
     P.N = N;
     P.M = M;
     P.nthreads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = std::getenv("MRA_HOST_THREADS")) P.nthreads = std::max(1, std::min(P.nthreads, std::atoi(e)));
     for (int b = 0; b < 2; ++b) {
       P.rows[b] = B.rows[b];
       P.xs[b] = B.xs[b];
