@@ -302,7 +302,7 @@ int upward_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m) {
   const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
   const int W = (m + 1) * r + 1, nb = (W - 1 + TB - 1) / TB;
   const int nt = nb * (nb + 1) / 2 + (W + TB - 1) / TB;   // lower tile pairs of the basis block + augmented-row jobs
-  MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<(unsigned)nn * nt, NT, smem_plain(), st>>>(c, list, nullptr, 0, nn)));
+  MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<(unsigned)((nn + 15) / 16 * 16) * nt, NT, smem_plain(), st>>>(c, list, nullptr, 0, nn, nt)));
   MRA_FOR_VEC(h, LAUNCH("node_factor", k_node_factor<V_><<<nn, NT, smem_factor(r), st>>>(c, list)));
   return MRA_OK;
 }
@@ -348,8 +348,8 @@ int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary)
     const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->sroots_off);
     const int W = h->shard_level * r + 1, nb = (W - 1 + TB - 1) / TB;
     const int nt = nb * (nb + 1) / 2 + (W + TB - 1) / TB;
-    MRA_FOR_VEC(h, LAUNCH("export_summary", k_assemble_A<V_><<<(unsigned)h->sroots.size() * nt, NT, smem_plain(), st>>>(
-                                                c, list, dev_summary, h->slot_base, (int)h->sroots.size())));
+    MRA_FOR_VEC(h, LAUNCH("export_summary", k_assemble_A<V_><<<(unsigned)((h->sroots.size() + 15) / 16 * 16) * nt, NT, smem_plain(), st>>>(
+                                                c, list, dev_summary, h->slot_base, (int)h->sroots.size(), nt)));
   }
   CU(cudaGetLastError());
   return MRA_OK;
