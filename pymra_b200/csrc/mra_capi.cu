@@ -31,7 +31,7 @@ struct Arena {
 
 struct Layout {
   size_t nodes, knot_rows, obs_rows, unobs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
-      mean, var, vnorm, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, tiles, ptiles, gather, chunks, ltiles, GTF, UTF, fold, VKL;
+      mean, var, vnorm, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, ptiles, gather, chunks, ltiles, GTF, UTF, fold, VKL;
   size_t total;
 };
 
@@ -51,8 +51,7 @@ struct mra_handle {
   // derived lists
   std::vector<std::vector<int>> internal_at;   // node ids per level
   std::vector<int> leaves;                     // node ids of leaves + orphans
-  std::vector<std::vector<int4>> tiles_at;     // 64-row tiles of internal nodes per level (predict pass)
-  std::vector<std::vector<int4>> ptiles_at;    // prior pass: the same plus gathered knot tiles (sharded runs)
+  std::vector<std::vector<int4>> ptiles_at;    // prior pass: 64-row tiles per level (+ gathered knot tiles when sharded)
   std::vector<int> gather_rows;                // row ids of the gathered tiles
   std::vector<int4> leaf_tiles;                // 64-row tiles of leaves / orphans (fused predict pass)
   std::vector<int4> fold_items;                // (node, ancestor level, row tile, column tile) of k_fold
@@ -73,7 +72,7 @@ struct mra_handle {
   Layout lay{};
   char* ws = nullptr;
   size_t ws_bytes = 0;
-  std::vector<size_t> list_off, tiles_off, ptiles_off;   // per level offsets (bytes) inside lay.lists / lay.tiles / lay.ptiles
+  std::vector<size_t> list_off, ptiles_off;   // per level offsets (bytes) inside lay.lists / lay.ptiles
   size_t leaves_off = 0;
   CovParams cov{0, 1.0, 1.0, 1.0, 1.0};
   double R = 1.0;
@@ -427,7 +426,6 @@ void build_lists(mra_handle* h) {
   const int nn = h->n_nodes, s = h->shard_level;
   const size_t nlev = (size_t)h->depth + 1;
   h->internal_at.assign(nlev, {});
-  h->tiles_at.assign(nlev, {});
   h->ptiles_at.assign(nlev, {});
   h->leaves.clear();
   h->gather_rows.clear();
@@ -437,7 +435,6 @@ void build_lists(mra_handle* h) {
     const int lv = h->level[node];
     for (int64_t r0 = 0; r0 < cnt; r0 += TB) {
       int4 t = make_int4(node, (int)(row0 + r0), (int)std::min<int64_t>(TB, cnt - r0), 0);
-      h->tiles_at[lv].push_back(t);
       h->ptiles_at[lv].push_back(t);
     }
   };
@@ -491,7 +488,6 @@ void build_lists(mra_handle* h) {
   }
   while (!h->internal_at.empty() && h->internal_at.back().empty()) {
     h->internal_at.pop_back();
-    h->tiles_at.pop_back();
     h->ptiles_at.pop_back();
   }
   h->leaf_tiles.clear();
@@ -815,14 +811,11 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.out_mean = ar.take(D * N);
   L.out_sd = ar.take(D * N);
   h->list_off.assign(h->internal_at.size(), 0);
-  h->tiles_off.assign(h->internal_at.size(), 0);
   h->ptiles_off.assign(h->internal_at.size(), 0);
-  size_t lo = 0, to = 0, po = 0;
+  size_t lo = 0, po = 0;
   for (size_t m = 0; m < h->internal_at.size(); ++m) {
     h->list_off[m] = lo;
     lo += (sizeof(int) * h->internal_at[m].size() + 255) & ~size_t(255);
-    h->tiles_off[m] = to;
-    to += (sizeof(int4) * h->tiles_at[m].size() + 255) & ~size_t(255);
     h->ptiles_off[m] = po;
     po += (sizeof(int4) * h->ptiles_at[m].size() + 255) & ~size_t(255);
   }
@@ -831,7 +824,6 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   h->sroots_off = lo;
   lo += (sizeof(int) * h->sroots.size() + 255) & ~size_t(255);
   L.lists = ar.take(std::max<size_t>(256, lo));
-  L.tiles = ar.take(std::max<size_t>(256, to));
   L.ptiles = ar.take(std::max<size_t>(256, po));
   L.gather = ar.take(std::max<size_t>(256, sizeof(int) * h->gather_rows.size()));
   L.chunks = ar.take(std::max<size_t>(256, sizeof(int2) * h->emit_chunks.size()));
@@ -879,9 +871,6 @@ int mra_upload_data(mra_handle* h, const double* locs, const double* obs, void* 
     if (!h->internal_at[m].empty())
       CU(cudaMemcpyAsync(h->ws + L.lists + h->list_off[m], h->internal_at[m].data(),
                          sizeof(int) * h->internal_at[m].size(), cudaMemcpyHostToDevice, st));
-    if (!h->tiles_at[m].empty())
-      CU(cudaMemcpyAsync(h->ws + L.tiles + h->tiles_off[m], h->tiles_at[m].data(),
-                         sizeof(int4) * h->tiles_at[m].size(), cudaMemcpyHostToDevice, st));
     if (!h->ptiles_at[m].empty())
       CU(cudaMemcpyAsync(h->ws + L.ptiles + h->ptiles_off[m], h->ptiles_at[m].data(),
                          sizeof(int4) * h->ptiles_at[m].size(), cudaMemcpyHostToDevice, st));
