@@ -87,6 +87,30 @@ int mra_build_structure_2d(const double *locs, int64_t n_locs, int32_t r, int32_
                            int64_t *node_knot_off, int64_t *knot_rows, int32_t *kinds_local,
                            int64_t *n_knot_rows_out, int64_t *perm, int32_t *dfs_index);
 
+/* Streaming variant of mra_build_structure_2d for regular trees (every node above level M has > 100 rows,
+ * > 100 knot candidates and four non-empty quadrants; M >= 1, n_locs >= 65536): the build runs on its own
+ * thread and reports progress, so the caller can start device work while the sequential legacy-RNG replay
+ * (MRANode.py:191-193 in DFS pre-order) is still running.  For a regular 4-ary tree the level-by-level node
+ * numbering is known in closed form (node k of level L has id (4^L-1)/3 + k, knot_off = id*r), hence
+ *   event 0      : node arrays, perm and the ROOT's knot_rows / kinds_local slots are final
+ *   event 1 + c  : knot_rows / kinds_local of every node in the subtree of the root's child c are final
+ *   event 5      : the build has ended (mt_key / mt_pos advanced exactly like mra_build_structure_2d)
+ * Slots that are not final yet read as 0.  mra_build_stream_wait blocks until the event has happened and
+ * returns MRA_OK, or the build's failure status -- MRA_BUILD_UNSUPPORTED for a tree outside this path, in
+ * which case mt_key / mt_pos are untouched and the output arrays are garbage.  All arrays stay owned by the
+ * caller and must outlive mra_build_stream_finish, which joins the thread, frees the job and returns the
+ * final status.  mra_build_stream_start itself returns MRA_BUILD_UNSUPPORTED (no job) for small inputs. */
+typedef struct mra_build_job mra_build_job;
+int mra_build_stream_start(const double *locs, int64_t n_locs, int32_t r, int32_t M, int32_t J,
+                           int32_t critDepth, uint32_t *mt_key, int32_t *mt_pos, int32_t max_nodes,
+                           int32_t *node_level, int32_t *node_parent, int32_t *node_kind,
+                           int64_t *node_row_start, int64_t *node_row_count, int32_t *node_child_start,
+                           int32_t *node_child_count, int64_t *node_knot_off, int64_t *knot_rows,
+                           int32_t *kinds_local, int64_t *perm, int32_t *dfs_index, mra_build_job **job);
+int mra_build_stream_wait(mra_build_job *job, int32_t event);
+int mra_build_stream_finish(mra_build_job *job, int32_t *n_nodes_out, int32_t *depth_out,
+                            int64_t *n_knot_rows_out);
+
 /* Tree/knot/partition indexing computed on the host (bit-exact to MRANode.py:23-98,
  * 179-242, 289-340); copied into the handle. */
 int mra_set_structure(mra_handle *h, const mra_structure *s);
@@ -102,6 +126,9 @@ int mra_bind_workspace(mra_handle *h, void *dev_workspace, size_t bytes);
 /* locs: [N*dim] row-major (MRATree locs), obs: [N] with NaN = missing (MRATree obs).
  * Host buffers; copied H2D on `stream` and permuted to tree order on the device. */
 int mra_upload_data(mra_handle *h, const double *locs, const double *obs, void *stream);
+/* Same, with locs / obs already copied to the device by the caller (caller's row order; read on `stream`
+ * before the call returns) -- lets the host->device copy start before the tree structure is known. */
+int mra_upload_data_dev(mra_handle *h, const double *dev_locs, const double *dev_obs, void *stream);
 
 /* Covariance descriptor introspected from the mt.ExpCovFun / mt.Matern32 closure, and the
  * nugget R (MRATree R / me_scale; must be a scalar, MRANode.py:85-88). */
@@ -140,6 +167,21 @@ int mra_set_shard(mra_handle *h, int32_t shard_level, const int8_t *node_role);
 int mra_summary_size(const mra_handle *h, int64_t *n_doubles);
 int mra_run_likelihood_local_async(mra_handle *h, void *stream, double *dev_summary);
 int mra_run_likelihood_top_async(mra_handle *h, void *stream, const double *dev_summary);
+
+/* Streamed likelihood evaluation on one GPU, for overlapping the device passes with a host build that is still
+ * drawing knots (mra_build_stream_*).  The subtrees of the root's children are the "parts" (mra_stream_parts;
+ * 0 = not available: sharded handle or a leaf root).  mra_stream_begin_async resets the pass and runs the
+ * root's prior level (MRANode.py:378-395 for the root), which needs the root's knots only;
+ * mra_stream_part_async(part) runs everything below the root for that subtree -- prior levels >= 1, leaf
+ * terms (and, when predictions are planned, the leaf part of the predict pass), upward pass down to level 1
+ * (MRANode.py:403-480) -- and mra_stream_end_async finishes the root (MRANode.py:432-468).  The result is
+ * bit-identical to mra_run_likelihood_async: the same kernels run on the same nodes, only in more launches.
+ * knot_rows: the caller's full knot_rows array (as in mra_structure) whose slots for the root / for the part
+ * are final by now; they are copied to the device before the launches (NULL = already uploaded). */
+int mra_stream_parts(const mra_handle *h, int32_t *n_parts);
+int mra_stream_begin_async(mra_handle *h, void *stream, const int64_t *knot_rows);
+int mra_stream_part_async(mra_handle *h, void *stream, int32_t part, const int64_t *knot_rows);
+int mra_stream_end_async(mra_handle *h, void *stream);
 
 /* Counters for bench.py: kernels launched by the last run_* call, and algorithmic FP64
  * flop of the last likelihood / predict pass as executed. */

@@ -14,6 +14,7 @@ RNG state, whole subtrees are sharded over the ranks' GPUs (pymra_b200/shard.py)
 the full likelihood and predictions (gather="root": predictions only on rank 0, None elsewhere).
 """
 import logging
+import os
 import time
 import weakref
 
@@ -21,7 +22,7 @@ import numpy as np
 
 from .covariance import introspect
 from .session import DeviceSession
-from .structure import build_structure
+from .structure import StreamBuild, build_structure
 
 logger = logging.getLogger("pymra_b200.MRATree")
 
@@ -111,17 +112,80 @@ class MRATree(object):
 
         locs_c = np.ascontiguousarray(locs, dtype=np.float64).reshape(N, self.d)
         t1 = time.perf_counter()
-        self._structure = build_structure(locs_c, r, M, J, critDepth)
-        t2 = time.perf_counter()
-        self._session = DeviceSession(self._structure, locs_c, obs_arr, want_predict=True, device=device, group=group,
-                                      gather=gather)
-        t3 = time.perf_counter()
-        self._mom = None
-        self._evaluate()
+        self.timings["args_and_cov"] = t1 - t0
+        self._session = None
+        if group is None and self.d == 2 and os.environ.get("PYMRA_B200_STREAM", "1") != "0":
+            self._construct_streamed(locs_c, obs_arr, r, M, J, critDepth, device)
+        if self._session is None:
+            t1 = time.perf_counter()
+            self._structure = build_structure(locs_c, r, M, J, critDepth)
+            t2 = time.perf_counter()
+            self._session = DeviceSession(self._structure, locs_c, obs_arr, want_predict=True, device=device,
+                                          group=group, gather=gather)
+            t3 = time.perf_counter()
+            self._mom = None
+            self._evaluate()
+            t4 = time.perf_counter()
+            self.timings.update(structure=t2 - t1, session_plan_upload=t3 - t2, likelihood=t4 - t3,
+                                **self._session.timings)
         self.root = _Root(self)
-        t4 = time.perf_counter()
-        self.timings.update(args_and_cov=t1 - t0, structure=t2 - t1, session_plan_upload=t3 - t2,
-                            likelihood=t4 - t3, **self._session.timings)
+
+    def _construct_streamed(self, locs_c, obs_arr, r, M, J, critDepth, device):
+        """Large regular 2-D trees on one GPU: the C++ builder runs on its own thread (StreamBuild) and the
+        device passes start as soon as the RNG-independent part of the tree (partition, permutation, the
+        root's knots) is known; each subtree of the root is evaluated when the sequential knot draw
+        (MRANode.py:191-193, DFS pre-order) has left it.  Same results and RNG consumption as the plain path;
+        leaves self._session = None (global RNG untouched) when the tree is outside this path."""
+        import torch
+        if not torch.cuda.is_available():
+            return                      # the plain path raises the "no CPU fallback" error
+        t0 = time.perf_counter()
+        sb = StreamBuild(locs_c, r, M, J, critDepth)
+        if not sb.started:
+            return
+        session = None
+        try:
+            # the inputs do not depend on the tree: copy them while the partition is running
+            dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+            staged = (torch.from_numpy(locs_c).to(dev), torch.from_numpy(np.ascontiguousarray(obs_arr).reshape(-1)).to(dev))
+            t1 = time.perf_counter()
+            if not sb.wait(0):
+                return
+            t2 = time.perf_counter()
+            session = DeviceSession(sb.structure, locs_c, obs_arr, want_predict=True, device=device, staged=staged)
+            del staged
+            session.set_params(self._cov, self._R)
+            t3 = time.perf_counter()
+            nparts = session.n_parts()
+            if nparts != 4:
+                return
+            session.stream_begin()
+            waits = 0.0
+            for c in range(nparts):
+                tw = time.perf_counter()
+                if not sb.wait(1 + c):
+                    return
+                waits += time.perf_counter() - tw
+                session.stream_part(c)
+            tw = time.perf_counter()
+            if not sb.finish():
+                return
+            waits += time.perf_counter() - tw
+            session.stream_end()
+            self._structure = sb.structure
+            self._session, session = session, None
+            self._d, self._u = self._session.fetch_likelihood()
+            self._mom = None
+            t4 = time.perf_counter()
+            self.timings.update(structure=t2 - t0, early_h2d=t1 - t0, session_plan_upload=t3 - t2,
+                                likelihood=t4 - t3, build_waits_in_likelihood=waits, streamed=1.0,
+                                **self._session.timings)
+        finally:
+            if session is not None:       # fell out of the streaming path after device work had started
+                import torch
+                torch.cuda.synchronize()
+                session.close()
+            sb.finish()
 
     @property
     def obs_inds(self):

@@ -36,10 +36,16 @@ SIGNATURES = {
     "mra_build_structure_2d": (C.c_int, [_pd, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.POINTER(C.c_uint32), _p32, C.c_int32, _p32, _p32, _p32, _p32, _p32,
                                          _p64, _p64, _p32, _p32, _p64, _p64, _p32, _p64, _p64, _p32]),
+    "mra_build_stream_start": (C.c_int, [_pd, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.POINTER(C.c_uint32), _p32, C.c_int32, _p32, _p32, _p32, _p64, _p64,
+                                         _p32, _p32, _p64, _p64, _p32, _p64, _p32, C.POINTER(C.c_void_p)]),
+    "mra_build_stream_wait": (C.c_int, [C.c_void_p, C.c_int32]),
+    "mra_build_stream_finish": (C.c_int, [C.c_void_p, _p32, _p32, _p64]),
     "mra_set_structure": (C.c_int, [C.c_void_p, C.POINTER(MraStructure)]),
     "mra_plan": (C.c_int, [C.c_void_p, _pd, C.c_int, C.POINTER(C.c_size_t)]),
     "mra_bind_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mra_upload_data": (C.c_int, [C.c_void_p, _pd, _pd, C.c_void_p]),
+    "mra_upload_data_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mra_set_cov": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "mra_set_nugget": (C.c_int, [C.c_void_p, C.c_double]),
     "mra_run_likelihood": (C.c_int, [C.c_void_p, C.c_void_p, _pd]),
@@ -51,6 +57,10 @@ SIGNATURES = {
     "mra_summary_size": (C.c_int, [C.c_void_p, _p64]),
     "mra_run_likelihood_local_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mra_run_likelihood_top_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mra_stream_parts": (C.c_int, [C.c_void_p, _p32]),
+    "mra_stream_begin_async": (C.c_int, [C.c_void_p, C.c_void_p, _p64]),
+    "mra_stream_part_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _p64]),
+    "mra_stream_end_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mra_last_launches": (C.c_int, [C.c_void_p, _p64]),
     "mra_last_flops": (C.c_int, [C.c_void_p, _pd, _pd]),
     "mra_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

@@ -61,6 +61,16 @@ struct mra_handle {
   int shard_level = 0;
   std::vector<int8_t> role;
   std::vector<int> sroots;                     // my subtree roots at the shard level
+  // streamed evaluation (mra_stream_*): the subtrees of the root's children ("parts") as ranges of the work lists
+  struct Range { int begin, count; };
+  int n_parts = 0;
+  std::vector<std::vector<Range>> part_nodes, part_tiles;   // [level][part] into internal_at / ptiles_at
+  std::vector<std::vector<Range>> part_leaves;              // [part] -> ranges of `leaves`
+  std::vector<std::vector<Range>> part_knots;               // [part] -> ranges of knot_rows
+  int stream_parts_done = 0;                                // bit mask of the parts run since mra_stream_begin_async
+  bool stream_open = false, leafq_done = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_event = nullptr;
   int slot_base = 0, n_slots = 0;
   size_t sroots_off = 0;
   std::vector<NodeDev> nodes;
@@ -293,16 +303,77 @@ int check_status(mra_handle* h, cudaStream_t st) {
   return MRA_OK;
 }
 
-int upward_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m) {
+using Range = mra_handle::Range;
+
+// assemble_A + node_factor for nodes [rg.begin, rg.begin + rg.count) of level m's list
+int upward_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m, Range rg) {
   const Layout& L = h->lay;
   const int r = h->r;
-  const int nn = (int)h->internal_at[m].size();
-  if (!nn) return MRA_OK;
-  const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
+  const int nn = rg.count;
+  if (nn <= 0) return MRA_OK;
+  const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]) + rg.begin;
   const int W = (m + 1) * r + 1, nb = (W - 1 + TB - 1) / TB;
   const int nt = nb * (nb + 1) / 2 + (W + TB - 1) / TB;   // lower tile pairs of the basis block + augmented-row jobs
   MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<(unsigned)((nn + 15) / 16 * 16) * nt, NT, smem_plain(), st>>>(c, list, nullptr, 0, nn, nt)));
   MRA_FOR_VEC(h, LAUNCH("node_factor", k_node_factor<V_><<<nn, NT, smem_factor(r), st>>>(c, list)));
+  return MRA_OK;
+}
+
+int upward_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m) {
+  return upward_level(h, st, c, m, Range{0, (int)h->internal_at[m].size()});
+}
+
+// knot_factor + prior_tiles for a range of level m's node list and the matching range of its tile list
+int prior_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m, Range nodes, Range tiles) {
+  const Layout& L = h->lay;
+  const int r = h->r;
+  if (nodes.count <= 0) return MRA_OK;
+  const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]) + nodes.begin;
+  MRA_FOR_VEC(h, LAUNCH("knot_factor", k_knot_factor<V_><<<nodes.count, NT, smem_knot(r), st>>>(c, list)));
+  if (tiles.count <= 0) return MRA_OK;
+  const int4* tl = reinterpret_cast<const int4*>(h->ws + L.ptiles + h->ptiles_off[m]) + tiles.begin;
+  MRA_FOR_VEC(h, LAUNCH("prior_tiles", k_prior_tiles<V_><<<tiles.count, NT, smem_prior(r), st>>>(c, tl, m)));
+  return MRA_OK;
+}
+
+// leaf terms of the likelihood (Gram of the observed rows, its Cholesky factor, UT) for a range of `leaves`
+int leaf_terms(mra_handle* h, cudaStream_t st, const DevCtx& c, Range rg) {
+  const Layout& L = h->lay;
+  const int nleaf = rg.count;
+  if (nleaf <= 0 || h->max_leaf_obs <= 0) return MRA_OK;
+  const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off) + rg.begin;
+  const int nbo = (h->max_leaf_obs + TB - 1) / TB;
+  const int nt1 = nbo * (nbo + 1) / 2;
+  MRA_FOR_VEC(h, LAUNCH("leaf_gram", k_leaf_gram<V_><<<(unsigned)nleaf * nt1, NT, smem_gram(), st>>>(c, leaf_list, 0, nleaf)));
+  MRA_FOR_VEC(h, LAUNCH("leaf_chol", k_leaf_factor<V_><<<nleaf, NT, smem_chol(h->max_leaf_obs), st>>>(c, leaf_list)));
+  const int nt3 = std::max(1, (h->max_leaf_W - 1 + TB - 1) / TB);
+  MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve_ut<V_><<<(unsigned)nleaf * nt3, NT, smem_solve(), st>>>(c, leaf_list, nt3)));
+  return MRA_OK;
+}
+
+// leaf part of the predict pass (QT and the leaf moments) for a range of `leaves`; needs leaf_terms only
+int leaf_predict_terms(mra_handle* h, cudaStream_t st, const DevCtx& c, Range rg) {
+  const Layout& L = h->lay;
+  const int nleaf = rg.count;
+  if (nleaf <= 0 || h->max_leaf_obs <= 0) return MRA_OK;
+  const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off) + rg.begin;
+  const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
+  const int nbu = (h->max_leaf_unobs + TB - 1) / TB;
+  if (nbu > 0)
+    MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<(unsigned)nleaf * nbu * nbo, NT, smem_gram(), st>>>(
+                                             c, leaf_list, 1, nleaf)));
+  MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", k_leaf_solve_qt<V_><<<(unsigned)nleaf * nbr, NT, smem_solve(), st>>>(
+                                            c, leaf_list, nbr)));
+  return MRA_OK;
+}
+
+int reset_pass(mra_handle* h, cudaStream_t st) {
+  const Layout& L = h->lay;
+  h->launches = 0;
+  h->leafq_done = false;
+  CU(cudaMemsetAsync(at<double>(h, L.dnode), 0, sizeof(double) * h->n_nodes, st));
+  CU(cudaMemsetAsync(at<int>(h, L.status), 0, sizeof(int), st));
+  CU(cudaMemsetAsync(at<double>(h, L.vnorm), 0, sizeof(double) * h->N, st));
   return MRA_OK;
 }
 
@@ -312,35 +383,19 @@ int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary)
   const Layout& L = h->lay;
   DevCtx c = make_ctx(h);
   const int r = h->r;
-  h->launches = 0;
-  CU(cudaMemsetAsync(at<double>(h, L.dnode), 0, sizeof(double) * h->n_nodes, st));
-  CU(cudaMemsetAsync(at<int>(h, L.status), 0, sizeof(int), st));
-  CU(cudaMemsetAsync(at<double>(h, L.vnorm), 0, sizeof(double) * h->N, st));
+  int rc = reset_pass(h, st);
+  if (rc) return rc;
   // ---- prior, top-down
   for (int m = 0; m < (int)h->internal_at.size(); ++m) {
-    const int nn = (int)h->internal_at[m].size();
-    if (!nn) continue;
-    const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]);
-    MRA_FOR_VEC(h, LAUNCH("knot_factor", k_knot_factor<V_><<<nn, NT, smem_knot(r), st>>>(c, list)));
-    const int ntile = (int)h->ptiles_at[m].size();
-    if (!ntile) continue;
-    const int4* tiles = reinterpret_cast<const int4*>(h->ws + L.ptiles + h->ptiles_off[m]);
-    MRA_FOR_VEC(h, LAUNCH("prior_tiles", k_prior_tiles<V_><<<ntile, NT, smem_prior(r), st>>>(c, tiles, m)));
+    rc = prior_level(h, st, c, m, Range{0, (int)h->internal_at[m].size()}, Range{0, (int)h->ptiles_at[m].size()});
+    if (rc) return rc;
   }
   // ---- leaves
-  const int nleaf = (int)h->leaves.size();
-  const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off);
-  if (nleaf && h->max_leaf_obs > 0) {
-    const int nbo = (h->max_leaf_obs + TB - 1) / TB;
-    const int nt1 = nbo * (nbo + 1) / 2;
-    MRA_FOR_VEC(h, LAUNCH("leaf_gram", k_leaf_gram<V_><<<(unsigned)nleaf * nt1, NT, smem_gram(), st>>>(c, leaf_list, 0, nleaf)));
-    MRA_FOR_VEC(h, LAUNCH("leaf_chol", k_leaf_factor<V_><<<nleaf, NT, smem_chol(h->max_leaf_obs), st>>>(c, leaf_list)));
-    const int nt3 = std::max(1, (h->max_leaf_W - 1 + TB - 1) / TB);
-    MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve_ut<V_><<<(unsigned)nleaf * nt3, NT, smem_solve(), st>>>(c, leaf_list, nt3)));
-  }
+  rc = leaf_terms(h, st, c, Range{0, (int)h->leaves.size()});
+  if (rc) return rc;
   // ---- upward, levels >= shard level
   for (int m = (int)h->internal_at.size() - 1; m >= h->shard_level; --m) {
-    int rc = upward_level(h, st, c, m);
+    rc = upward_level(h, st, c, m);
     if (rc) return rc;
   }
   if (h->shard_level > 0 && !h->sroots.empty()) {
@@ -386,16 +441,10 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
   DevCtx c = make_ctx(h);
   const int r = h->r;
   if (!h->pred_done) {
-    const int nleaf = (int)h->leaves.size();
-    const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off);
-    if (h->max_leaf_obs > 0) {
-      const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
-      const int nbu = (h->max_leaf_unobs + TB - 1) / TB;
-      if (nbu > 0)
-        MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<(unsigned)nleaf * nbu * nbo, NT, smem_gram(), st>>>(
-                                                 c, leaf_list, 1, nleaf)));
-      MRA_FOR_VEC(h, LAUNCH("leaf_solve_Q", k_leaf_solve_qt<V_><<<(unsigned)nleaf * nbr, NT, smem_solve(), st>>>(
-                                                c, leaf_list, nbr)));
+    if (!h->leafq_done) {
+      int rc = leaf_predict_terms(h, st, c, Range{0, (int)h->leaves.size()});
+      if (rc) return rc;
+      h->leafq_done = true;
     }
     if (!h->fold_items.empty())
       MRA_FOR_VEC(h, LAUNCH("fold", k_fold<V_><<<(unsigned)h->fold_items.size(), NT, GS1, st>>>(
@@ -494,6 +543,54 @@ void build_lists(mra_handle* h) {
   for (int n : h->leaves)
     for (int64_t r0 = 0; r0 < h->row_count[n]; r0 += TB)
       h->leaf_tiles.push_back(make_int4(n, (int)(h->row_start[n] + r0), (int)std::min<int64_t>(TB, h->row_count[n] - r0), 0));
+  // parts for the streamed evaluation: the subtree of every child of the root is a contiguous range of each list
+  h->n_parts = 0;
+  h->part_nodes.clear();
+  h->part_tiles.clear();
+  h->part_leaves.clear();
+  h->part_knots.clear();
+  if (s == 0 && nn > 1 && h->kind[0] == KIND_INTERNAL && !h->internal_at.empty()) {
+    const int np = h->child_count[0], c0 = h->child_start[0];
+    std::vector<int> part_of((size_t)nn, -1);
+    for (int n = 1; n < nn; ++n) part_of[n] = h->parent[n] == 0 ? n - c0 : part_of[h->parent[n]];
+    h->n_parts = np;
+    const size_t nl = h->internal_at.size();
+    h->part_nodes.assign(nl, std::vector<Range>(np, Range{0, 0}));
+    h->part_tiles.assign(nl, std::vector<Range>(np, Range{0, 0}));
+    h->part_leaves.assign(np, {});
+    h->part_knots.assign(np, {});
+    auto extend = [](Range& rg, int i) {
+      if (rg.count == 0) rg.begin = i;
+      ++rg.count;
+    };
+    bool ok = true;
+    for (size_t m = 1; m < nl; ++m) {
+      int last = -1;
+      for (int i = 0; i < (int)h->internal_at[m].size(); ++i) {
+        const int n = h->internal_at[m][i], pp = part_of[n];
+        if (pp < last) ok = false;
+        last = pp;
+        extend(h->part_nodes[m][pp], i);
+        std::vector<Range>& kr = h->part_knots[pp];
+        const int ko = (int)h->knot_off[n];
+        if (!kr.empty() && kr.back().begin + kr.back().count == ko) kr.back().count += h->r;
+        else kr.push_back(Range{ko, h->r});
+      }
+      last = -1;
+      for (int i = 0; i < (int)h->ptiles_at[m].size(); ++i) {
+        const int pp = part_of[h->ptiles_at[m][i].x];
+        if (pp < last) ok = false;
+        last = pp;
+        extend(h->part_tiles[m][pp], i);
+      }
+    }
+    for (int i = 0; i < (int)h->leaves.size(); ++i) {
+      std::vector<Range>& lr = h->part_leaves[part_of[h->leaves[i]]];
+      if (!lr.empty() && lr.back().begin + lr.back().count == i) ++lr.back().count;
+      else lr.push_back(Range{i, 1});
+    }
+    if (!ok) h->n_parts = 0;      // cannot happen with level-by-level numbering; streaming is refused then
+  }
 }
 
 }  // namespace
@@ -521,6 +618,18 @@ int mra_create(mra_handle** out, int device) {
 }
 
 int mra_destroy(mra_handle* h) {
+  if (h && h->copy_stream) {
+    cudaSetDevice(h->device);
+    cudaEventDestroy(h->copy_event);
+    cudaStreamDestroy(h->copy_stream);
+  }
+  if (h) {
+    for (auto& rec : h->prof_recs) {
+      cudaEventDestroy(rec.e0);
+      cudaEventDestroy(rec.e1);
+    }
+    for (auto& e : h->event_pool) cudaEventDestroy(e);
+  }
   delete h;
   return MRA_OK;
 }
@@ -851,8 +960,9 @@ int mra_bind_workspace(mra_handle* h, void* dev_workspace, size_t bytes) {
   return MRA_OK;
 }
 
-int mra_upload_data(mra_handle* h, const double* locs, const double* obs, void* stream) {
-  if (!h || !locs || !obs) return MRA_ERR_ARG;
+// structure tables + inputs; the inputs come from host buffers (locs, obs) or are already on the device (dev_*)
+static int upload_impl(mra_handle* h, const double* locs, const double* obs, const double* dev_locs,
+                       const double* dev_obs, void* stream) {
   if (!h->bound) return fail(h, MRA_ERR_STATE, "mra_bind_workspace must be called first");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const Layout& L = h->lay;
@@ -893,16 +1003,30 @@ int mra_upload_data(mra_handle* h, const double* locs, const double* obs, void* 
   if (!h->leaves.empty())
     CU(cudaMemcpyAsync(h->ws + L.lists + h->leaves_off, h->leaves.data(), sizeof(int) * h->leaves.size(),
                        cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(h->ws + L.stage_locs, locs, sizeof(double) * N * h->dim, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(h->ws + L.stage_obs, obs, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+  if (!dev_locs) {
+    CU(cudaMemcpyAsync(h->ws + L.stage_locs, locs, sizeof(double) * N * h->dim, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->ws + L.stage_obs, obs, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    dev_locs = at<double>(h, L.stage_locs);
+    dev_obs = at<double>(h, L.stage_obs);
+  }
   k_permute_inputs<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(
-      at<double>(h, L.stage_locs), at<double>(h, L.stage_obs), at<int>(h, L.perm), (int)N, h->dim,
+      dev_locs, dev_obs, at<int>(h, L.perm), (int)N, h->dim,
       at<double>(h, L.xs), at<double>(h, L.ys), at<double>(h, L.yobs));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(st));   // host vectors may change after return
   h->uploaded = true;
   h->lik_done = h->pred_done = false;
   return MRA_OK;
+}
+
+int mra_upload_data(mra_handle* h, const double* locs, const double* obs, void* stream) {
+  if (!h || !locs || !obs) return MRA_ERR_ARG;
+  return upload_impl(h, locs, obs, nullptr, nullptr, stream);
+}
+
+int mra_upload_data_dev(mra_handle* h, const double* dev_locs, const double* dev_obs, void* stream) {
+  if (!h || !dev_locs || !dev_obs) return MRA_ERR_ARG;
+  return upload_impl(h, nullptr, nullptr, dev_locs, dev_obs, stream);
 }
 
 int mra_set_cov(mra_handle* h, int family, double length_scale, double sig) {
@@ -993,6 +1117,98 @@ int mra_run_likelihood_top_async(mra_handle* h, void* stream, const double* dev_
   int rc = ready_to_run(h);
   if (rc) return rc;
   return launch_likelihood_top(h, static_cast<cudaStream_t>(stream), dev_summary);
+}
+
+int mra_stream_parts(const mra_handle* h, int32_t* n_parts) {
+  if (!h || !n_parts) return MRA_ERR_ARG;
+  *n_parts = h->shard_level == 0 ? h->n_parts : 0;
+  return MRA_OK;
+}
+
+// uploads ranges of the caller's knot_rows (tree-order row ids) on the copy stream and makes `st` wait for them
+static int upload_knot_ranges(mra_handle* h, cudaStream_t st, const int64_t* knot_rows, const std::vector<Range>& ranges) {
+  if (!knot_rows || ranges.empty()) return MRA_OK;
+  if (!h->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->copy_event, cudaEventDisableTiming));
+  }
+  for (const Range& rg : ranges) {
+    for (int i = rg.begin; i < rg.begin + rg.count; ++i) {
+      if (knot_rows[i] < 0 || knot_rows[i] >= h->N) return fail(h, MRA_ERR_ARG, "knot row out of range");
+      h->knot_rows[i] = (int)knot_rows[i];
+    }
+    CU(cudaMemcpyAsync(h->ws + h->lay.knot_rows + sizeof(int) * (size_t)rg.begin, h->knot_rows.data() + rg.begin,
+                       sizeof(int) * (size_t)rg.count, cudaMemcpyHostToDevice, h->copy_stream));
+  }
+  CU(cudaEventRecord(h->copy_event, h->copy_stream));
+  CU(cudaStreamWaitEvent(st, h->copy_event, 0));
+  return MRA_OK;
+}
+
+int mra_stream_begin_async(mra_handle* h, void* stream, const int64_t* knot_rows) {
+  if (!h) return MRA_ERR_ARG;
+  if (h->shard_level > 0 || h->n_parts <= 0) return fail(h, MRA_ERR_STATE, "streamed evaluation needs an unsharded tree with an internal root");
+  int rc = ready_to_run(h);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DevCtx c = make_ctx(h);
+  h->lik_done = h->pred_done = false;
+  rc = reset_pass(h, st);
+  if (rc) return rc;
+  rc = upload_knot_ranges(h, st, knot_rows, std::vector<Range>{Range{(int)h->knot_off[0], h->r}});
+  if (rc) return rc;
+  rc = prior_level(h, st, c, 0, Range{0, (int)h->internal_at[0].size()}, Range{0, (int)h->ptiles_at[0].size()});
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  h->stream_open = true;
+  h->stream_parts_done = 0;
+  return MRA_OK;
+}
+
+int mra_stream_part_async(mra_handle* h, void* stream, int32_t part, const int64_t* knot_rows) {
+  if (!h) return MRA_ERR_ARG;
+  if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
+  if (part < 0 || part >= h->n_parts) return fail(h, MRA_ERR_ARG, "part out of range");
+  if (h->stream_parts_done & (1 << part)) return fail(h, MRA_ERR_STATE, "part already evaluated");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  DevCtx c = make_ctx(h);
+  int rc = upload_knot_ranges(h, st, knot_rows, h->part_knots[part]);
+  if (rc) return rc;
+  const int nl = (int)h->internal_at.size();
+  for (int m = 1; m < nl; ++m) {
+    rc = prior_level(h, st, c, m, h->part_nodes[m][part], h->part_tiles[m][part]);
+    if (rc) return rc;
+  }
+  for (const Range& rg : h->part_leaves[part]) {
+    rc = leaf_terms(h, st, c, rg);
+    if (rc) return rc;
+    if (h->want_predict) {
+      rc = leaf_predict_terms(h, st, c, rg);
+      if (rc) return rc;
+    }
+  }
+  for (int m = nl - 1; m >= 1; --m) {
+    rc = upward_level(h, st, c, m, h->part_nodes[m][part]);
+    if (rc) return rc;
+  }
+  CU(cudaGetLastError());
+  h->stream_parts_done |= 1 << part;
+  return MRA_OK;
+}
+
+int mra_stream_end_async(mra_handle* h, void* stream) {
+  if (!h) return MRA_ERR_ARG;
+  if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
+  if (h->stream_parts_done != (1 << h->n_parts) - 1) return fail(h, MRA_ERR_STATE, "not every part has been evaluated");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  DevCtx c = make_ctx(h);
+  int rc = upward_level(h, st, c, 0);
+  if (rc) return rc;
+  h->stream_open = false;
+  h->leafq_done = h->want_predict;
+  return launch_likelihood_top(h, st, nullptr);     // shard_level == 0: only the final reduction
 }
 
 int mra_fetch_likelihood(mra_handle* h, void* stream, double out[2]) {

@@ -16,7 +16,9 @@
 #include <algorithm>
 #include <atomic>
 #include <functional>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <cstdint>
 #include <cstdlib>
@@ -487,10 +489,13 @@ struct Partitioner {
   std::unique_ptr<std::atomic<int>[]> sub_ready;
   std::atomic<int> ready{0};
   std::atomic<int> failed{0};
+  std::atomic<int> all_done{0};              // partition finished (and, in stream mode, the output arrays filled)
   struct PNode {
     int64_t s, e;
     double sx, sy;
   };
+  std::vector<std::vector<PNode>> level_nodes;   // [L][index inside level]: every node's row range
+  std::function<void()> on_done;                 // stream mode: fills the caller's node arrays / perm
   static constexpr int64_t BIG = 1 << 18;
 
   // codes and counts of positions [a, b) of a node with means (mx, my)
@@ -650,12 +655,16 @@ struct Partitioner {
       if (failed.load()) return;
       build_bits(sub[k][L - S], root.s, root.e, 1);
       cur.swap(next);
+      std::copy(cur.begin(), cur.end(), level_nodes[L + 1].begin() + (size_t)k * cur.size());
     }
   }
 
   void run(double sx0, double sy0) {
     std::vector<PNode> cur{PNode{0, N, sx0, sy0}}, next;
+    level_nodes.assign(M + 1, {});
+    for (int L = 0; L <= M; ++L) level_nodes[L].resize((size_t)1 << (2 * L));
     for (int L = 0; L < S; ++L) {
+      level_nodes[L] = cur;
       next.assign(cur.size() * 4, PNode{0, 0, 0.0, 0.0});
       const int b = L & 1;
       // big nodes one after the other (all threads inside), the rest in parallel
@@ -674,6 +683,7 @@ struct Partitioner {
       cur.swap(next);
     }
     const int nsub = (int)sub.size();
+    if (!failed.load()) level_nodes[S] = cur;
     if (!failed.load() && S < M) {
       // the subtrees below level S are independent: workers take them in DFS order, so the RNG replay (which
       // visits them in the same order) rarely has to wait
@@ -691,14 +701,59 @@ struct Partitioner {
     if (failed.load()) {
       ready.store(M + 1, std::memory_order_release);
       for (int k = 0; k < nsub; ++k) sub_ready[k].store(1, std::memory_order_release);
+    } else if (on_done) {
+      on_done();
     }
+    all_done.store(1, std::memory_order_release);
   }
+};
+
+// Stream mode (mra_build_structure_2d_stream): for a regular tree the BFS numbering is known in closed form,
+// so node arrays and the permutation are final as soon as the partition is (stage 0), and the knot rows of a
+// level-1 subtree are final when the RNG replay leaves it (stage 1) -- the caller can start device work on a
+// finished subtree while the replay continues with the next one.
+struct StreamOut {
+  std::function<void(int)> cb;          // cb(0): stage 0; cb(1 + c): level-1 subtree c finished
+  int64_t* knot_rows = nullptr;
+  int32_t* kinds_local = nullptr;
+  int32_t* dfs_index = nullptr;
+  std::vector<int64_t> level_off;      // BFS id of the first node of every level
+  bool stage0_fired = false;
+  int dfs_counter = 0;
+  std::vector<KEnt> root_knots;        // the root's own knots (position at level 0, slot)
 };
 
 struct RankBuilder {
   Builder* B;
   Partitioner* P;
   int M;
+  StreamOut* so = nullptr;
+
+  const LevelBits& bits_for(int level, int64_t idx) const {
+    if (level < P->S) return P->lv[level];
+    return P->sub[idx >> (2 * (level - P->S))][level - P->S];
+  }
+
+  // tree-order rows of the root's knots by walking the finished bit planes, then the stage-0 callback
+  void fire_stage0() {
+    so->stage0_fired = true;
+    for (const KEnt& k : so->root_knots) {
+      int64_t x = k.pos, s0 = 0, e0 = P->N, idx = 0;
+      for (int L = 0; L < M; ++L) {
+        const LevelBits& lb = bits_for(L, idx);
+        const int c = lb.code(x);
+        int64_t off = s0;
+        for (int cc = 0; cc < c; ++cc) off += lb.rank(cc, e0) - lb.rank(cc, s0);
+        const int64_t cnt = lb.rank(c, e0) - lb.rank(c, s0);
+        x = off + lb.rank(c, x) - lb.rank(c, s0);
+        s0 = off;
+        e0 = off + cnt;
+        idx = 4 * idx + c;
+      }
+      so->knot_rows[k.id] = x;
+    }
+    if (so->cb) so->cb(0);
+  }
 
   // idx: index of the node inside its level (regular 4-ary tree), which also names its level-S subtree
   void visit(int parent, int level, int64_t idx, int64_t s, int64_t e, int levels_left, const std::vector<KEnt>& kp) {
@@ -706,6 +761,11 @@ struct RankBuilder {
     if (b.status) return;
     const int me = (int)b.rec.size();
     b.rec.push_back(Rec{level, parent, MRA_NODE_LEAF, s, e - s, -1, 0, -1});
+    if (so) {
+      so->dfs_index[so->level_off[level] + idx] = so->dfs_counter++;
+      if (!so->stage0_fired && level > 0 && P->all_done.load(std::memory_order_acquire) && !P->failed.load())
+        fire_stage0();
+    }
     const int64_t n = e - s;
     const int64_t n_nk = n - (int64_t)kp.size();
     const bool internal = levels_left > 0 && n_nk > std::max(b.r, b.J);
@@ -714,7 +774,12 @@ struct RankBuilder {
         b.status = 1;
         return;
       }
-      for (const KEnt& k : kp) b.knot_tree_row[k.id] = (int32_t)(s + k.pos);
+      if (so) {
+        for (const KEnt& k : kp)
+          if (k.id >= b.r || !so->stage0_fired) so->knot_rows[k.id] = s + k.pos;   // root slots are final after stage 0
+      } else {
+        for (const KEnt& k : kp) b.knot_tree_row[k.id] = (int32_t)(s + k.pos);
+      }
       return;
     }
     if (n_nk <= 100 || n <= 100) {
@@ -737,9 +802,16 @@ struct RankBuilder {
           ++j;
           ++pos;
         }
-        const int32_t id = (int32_t)b.kinds_local.size();
-        b.kinds_local.push_back(pos);
-        b.knot_tree_row.push_back(-1);
+        int32_t id;
+        if (so) {            // slot in the caller's arrays: BFS id of this node * r + t
+          id = (int32_t)((so->level_off[level] + idx) * b.r + t);
+          so->kinds_local[id] = pos;
+          if (level == 0) so->root_knots.push_back(KEnt{pos, id});
+        } else {
+          id = (int32_t)b.kinds_local.size();
+          b.kinds_local.push_back(pos);
+          b.knot_tree_row.push_back(-1);
+        }
         mk.push_back(KEnt{pos, id});
       }
       for (; j < kp.size(); ++j) mk.push_back(kp[j]);
@@ -784,33 +856,31 @@ struct RankBuilder {
       if (c == 0) b.rec[me].first_child = (int)b.rec.size();
       visit(me, level + 1, 4 * idx + c, off[c], off[c] + cnt[c], levels_left - 1, ckp[c]);
       if (b.status) return;
+      if (so && level == 0) {          // a level-1 subtree is complete: its knot rows are final
+        while (!P->all_done.load(std::memory_order_acquire)) std::this_thread::yield();
+        if (P->failed.load()) {
+          b.status = 1;
+          return;
+        }
+        if (!so->stage0_fired) fire_stage0();
+        if (so->cb) so->cb(1 + c);
+      }
     }
     if (fork) b.rng = saved;
   }
 };
 
-}  // namespace
+// Scratch buffers shared by all builds of this process (one build at a time).
+Pool g_pool;
+std::mutex g_pool_mu;
 
-extern "C" {
-
-int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_t M, int32_t J,
-                           int32_t critDepth, uint32_t* mt_key, int32_t* mt_pos, int32_t max_nodes,
-                           int32_t* n_nodes_out, int32_t* depth_out, int32_t* node_level, int32_t* node_parent,
-                           int32_t* node_kind, int64_t* node_row_start, int64_t* node_row_count,
-                           int32_t* node_child_start, int32_t* node_child_count, int64_t* node_knot_off,
-                           int64_t* knot_rows, int32_t* kinds_local, int64_t* n_knot_rows_out, int64_t* perm,
-                           int32_t* dfs_index) {
-  if (!locs || n_locs <= 0 || n_locs >= (int64_t(1) << 31) || r < 1 || !mt_key || !mt_pos) return MRA_ERR_ARG;
-  if (r > 256) return MRA_BUILD_UNSUPPORTED;
-  static thread_local Pool pool;
-  Builder B;
-  B.N = n_locs;
+bool prepare_builder(Builder& B, Pool& pool, int64_t N, int r, int J, int critDepth, const uint32_t* mt_key, int mt_pos) {
+  B.N = N;
   B.r = r;
   B.J = J;
   B.critDepth = critDepth;
   std::memcpy(B.rng.key, mt_key, sizeof(uint32_t) * 624);
-  B.rng.pos = *mt_pos;
-  const int64_t N = n_locs;
+  B.rng.pos = mt_pos;
   for (int b = 0; b < 2; ++b) {
     B.rows[b] = pool.rows[b].get(N);
     B.xs[b] = pool.xs[b].get(N);
@@ -829,9 +899,162 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
     if (B.bits && (fresh || pool.bits_n < nb)) std::memset(B.bits, 0, sizeof(uint64_t) * pool.bits.cap);
     pool.bits_n = pool.bits.cap;
   }
-  if (!B.rows[0] || !B.rows[1] || !B.xs[0] || !B.xs[1] || !B.ys[0] || !B.ys[1] || !B.scratch || !B.draws ||
-      !B.perm || !B.code || !B.slot_of || !B.bits)
-    return MRA_ERR_NOMEM;
+  return B.rows[0] && B.rows[1] && B.xs[0] && B.xs[1] && B.ys[0] && B.ys[1] && B.scratch && B.draws && B.perm &&
+         B.code && B.slot_of && B.bits;
+}
+
+void setup_partitioner(Partitioner& P, Builder& B, int64_t N, int M) {
+  P.N = N;
+  P.M = M;
+  P.nthreads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  if (const char* e = std::getenv("MRA_HOST_THREADS")) P.nthreads = std::max(1, std::min(P.nthreads, std::atoi(e)));
+  for (int b = 0; b < 2; ++b) {
+    P.rows[b] = B.rows[b];
+    P.xs[b] = B.xs[b];
+    P.ys[b] = B.ys[b];
+  }
+  P.code = B.code;
+  P.S = std::min(2, (int)M);
+  P.lv.resize(P.S);
+  const int nsub = P.S < M ? 1 << (2 * P.S) : 0;
+  P.sub.assign(nsub, std::vector<LevelBits>(M - P.S));
+  P.sub_ready.reset(new std::atomic<int>[std::max(1, nsub)]);
+  for (int k = 0; k < nsub; ++k) P.sub_ready[k].store(0);
+}
+
+}  // namespace
+
+// Streaming build (mra_build_stream_*): the build runs on its own thread and reports progress events.
+struct mra_build_job {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  int fired = 0;          // events 0 .. fired-1 have happened (0: partition ready, 1 + c: level-1 subtree c final)
+  int status = MRA_OK;    // valid once done
+  bool done = false;
+  int32_t n_nodes = 0, depth = 0;
+  int64_t n_knot_rows = 0;
+};
+
+namespace {
+
+struct StreamArgs {
+  const double* locs;
+  int64_t N;
+  int32_t r, M, J, critDepth;
+  uint32_t* mt_key;
+  int32_t* mt_pos;
+  int32_t *node_level, *node_parent, *node_kind;
+  int64_t *node_row_start, *node_row_count;
+  int32_t *node_child_start, *node_child_count;
+  int64_t *node_knot_off, *knot_rows;
+  int32_t* kinds_local;
+  int64_t* perm;
+  int32_t* dfs_index;
+};
+
+void stream_body(mra_build_job* job, StreamArgs a) {
+  int status = MRA_OK;
+  {
+    std::lock_guard<std::mutex> pool_lock(g_pool_mu);
+    Builder B;
+    if (!prepare_builder(B, g_pool, a.N, a.r, a.J, a.critDepth, a.mt_key, *a.mt_pos)) {
+      status = MRA_ERR_NOMEM;
+    } else {
+      const int64_t N = a.N;
+      const int M = a.M;
+      Partitioner P;
+      setup_partitioner(P, B, N, M);
+      StreamOut so;
+      so.knot_rows = a.knot_rows;
+      so.kinds_local = a.kinds_local;
+      so.dfs_index = a.dfs_index;
+      so.level_off.assign(M + 2, 0);
+      for (int L = 0; L <= M; ++L) so.level_off[L + 1] = so.level_off[L] + ((int64_t)1 << (2 * L));
+      so.cb = [job](int ev) {
+        {
+          std::lock_guard<std::mutex> lk(job->mu);
+          job->fired = ev + 1;
+        }
+        job->cv.notify_all();
+      };
+      // node arrays in closed form (regular 4-ary tree, BFS ids) and the permutation, on the partition thread
+      P.on_done = [&] {
+        for (int L = 0; L <= M; ++L) {
+          const int64_t cnt = (int64_t)1 << (2 * L);
+          for (int64_t idx = 0; idx < cnt; ++idx) {
+            const int64_t id = so.level_off[L] + idx;
+            const Partitioner::PNode& nd = P.level_nodes[L][idx];
+            a.node_level[id] = L;
+            a.node_parent[id] = L ? (int32_t)(so.level_off[L - 1] + idx / 4) : -1;
+            a.node_kind[id] = L < M ? MRA_NODE_INTERNAL : MRA_NODE_LEAF;
+            a.node_row_start[id] = nd.s;
+            a.node_row_count[id] = nd.e - nd.s;
+            a.node_child_start[id] = L < M ? (int32_t)(so.level_off[L + 1] + 4 * idx) : -1;
+            a.node_child_count[id] = L < M ? 4 : 0;
+            a.node_knot_off[id] = L < M ? id * a.r : -1;
+          }
+        }
+        const int32_t* src = P.rows[M & 1];
+        int64_t* dst = a.perm;
+        const int64_t nchunk = 64, step = (N + nchunk - 1) / nchunk;
+        run_parallel(P.nthreads, nchunk, [&](int64_t k) {
+          const int64_t i0 = k * step, i1 = std::min(N, i0 + step);
+          for (int64_t i = i0; i < i1; ++i) dst[i] = src[i];
+        });
+      };
+      double sx = 0.0, sy = 0.0;
+      std::thread worker([&] {
+        for (int64_t i = 0; i < N; ++i) {
+          B.rows[0][i] = (int32_t)i;
+          const double x = a.locs[2 * i], y = a.locs[2 * i + 1];
+          B.xs[0][i] = x;
+          B.ys[0][i] = y;
+          sx += x;
+          sy += y;
+        }
+        P.run(sx, sy);
+      });
+      RankBuilder RB{&B, &P, M, &so};
+      RB.visit(-1, 0, 0, 0, N, M, std::vector<KEnt>());
+      worker.join();
+      if (B.status || P.failed.load()) {
+        status = MRA_BUILD_UNSUPPORTED;     // ragged tree: the caller's RNG state has not been touched
+      } else {
+        std::memcpy(a.mt_key, B.rng.key, sizeof(uint32_t) * 624);
+        *a.mt_pos = B.rng.pos;
+        job->n_nodes = (int32_t)so.level_off[M + 1];
+        job->depth = M;
+        job->n_knot_rows = so.level_off[M] * a.r;
+      }
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lk(job->mu);
+    job->status = status;
+    job->done = true;
+  }
+  job->cv.notify_all();
+}
+
+}  // namespace
+
+extern "C" {
+
+int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_t M, int32_t J,
+                           int32_t critDepth, uint32_t* mt_key, int32_t* mt_pos, int32_t max_nodes,
+                           int32_t* n_nodes_out, int32_t* depth_out, int32_t* node_level, int32_t* node_parent,
+                           int32_t* node_kind, int64_t* node_row_start, int64_t* node_row_count,
+                           int32_t* node_child_start, int32_t* node_child_count, int64_t* node_knot_off,
+                           int64_t* knot_rows, int32_t* kinds_local, int64_t* n_knot_rows_out, int64_t* perm,
+                           int32_t* dfs_index) {
+  if (!locs || n_locs <= 0 || n_locs >= (int64_t(1) << 31) || r < 1 || !mt_key || !mt_pos) return MRA_ERR_ARG;
+  if (r > 256) return MRA_BUILD_UNSUPPORTED;
+  std::lock_guard<std::mutex> pool_lock(g_pool_mu);
+  Pool& pool = g_pool;
+  Builder B;
+  if (!prepare_builder(B, pool, n_locs, r, J, critDepth, mt_key, *mt_pos)) return MRA_ERR_NOMEM;
+  const int64_t N = n_locs;
   double sx = 0.0, sy = 0.0;
   // level-0 arrays and the root's column sums (sequential, np.mean's order)
   auto init_level0 = [&] {
@@ -849,24 +1072,7 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
   if (M >= 1 && N >= (int64_t)1 << 16) {
     // threaded two-phase build; falls back to the serial DFS below when the tree is not regular
     Partitioner P;
-    P.N = N;
-    P.M = M;
-    P.nthreads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
-    if (const char* e = std::getenv("MRA_HOST_THREADS")) P.nthreads = std::max(1, std::min(P.nthreads, std::atoi(e)));
-    for (int b = 0; b < 2; ++b) {
-      P.rows[b] = B.rows[b];
-      P.xs[b] = B.xs[b];
-      P.ys[b] = B.ys[b];
-    }
-    P.code = B.code;
-    P.S = std::min(2, (int)M);
-    P.lv.resize(P.S);
-    {
-      const int nsub = P.S < M ? 1 << (2 * P.S) : 0;
-      P.sub.assign(nsub, std::vector<LevelBits>(M - P.S));
-      P.sub_ready.reset(new std::atomic<int>[std::max(1, nsub)]);
-      for (int k = 0; k < nsub; ++k) P.sub_ready[k].store(0);
-    }
+    setup_partitioner(P, B, N, M);
     std::thread worker([&] {     // the root's draws need nothing but N: the RNG replay starts right away
       init_level0();
       P.run(sx, sy);
@@ -937,6 +1143,62 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
   std::memcpy(mt_key, B.rng.key, sizeof(uint32_t) * 624);
   *mt_pos = B.rng.pos;
   return MRA_OK;
+}
+
+int mra_build_stream_start(const double* locs, int64_t n_locs, int32_t r, int32_t M, int32_t J, int32_t critDepth,
+                           uint32_t* mt_key, int32_t* mt_pos, int32_t max_nodes, int32_t* node_level,
+                           int32_t* node_parent, int32_t* node_kind, int64_t* node_row_start,
+                           int64_t* node_row_count, int32_t* node_child_start, int32_t* node_child_count,
+                           int64_t* node_knot_off, int64_t* knot_rows, int32_t* kinds_local, int64_t* perm,
+                           int32_t* dfs_index, mra_build_job** job_out) {
+  if (!job_out) return MRA_ERR_ARG;
+  *job_out = nullptr;
+  if (!locs || n_locs <= 0 || n_locs >= (int64_t(1) << 31) || r < 1 || !mt_key || !mt_pos || !node_level ||
+      !node_parent || !node_kind || !node_row_start || !node_row_count || !node_child_start || !node_child_count ||
+      !node_knot_off || !knot_rows || !kinds_local || !perm || !dfs_index)
+    return MRA_ERR_ARG;
+  if (r > 256 || M < 1 || M > 12 || n_locs < ((int64_t)1 << 16)) return MRA_BUILD_UNSUPPORTED;
+  int64_t nn = 0;
+  for (int L = 0; L <= M; ++L) nn += (int64_t)1 << (2 * L);
+  if (nn > max_nodes) return MRA_ERR_NOMEM;
+  mra_build_job* job = new (std::nothrow) mra_build_job();
+  if (!job) return MRA_ERR_NOMEM;
+  // slots of knots that are not final yet read as row 0 (a valid row id)
+  std::memset(knot_rows, 0, sizeof(int64_t) * (size_t)(nn - ((int64_t)1 << (2 * M))) * r);
+  StreamArgs a{locs, n_locs, r, M, J, critDepth, mt_key, mt_pos, node_level, node_parent, node_kind,
+               node_row_start, node_row_count, node_child_start, node_child_count, node_knot_off, knot_rows,
+               kinds_local, perm, dfs_index};
+  try {
+    job->th = std::thread(stream_body, job, a);
+  } catch (...) {
+    delete job;
+    return MRA_ERR_NOMEM;
+  }
+  *job_out = job;
+  return MRA_OK;
+}
+
+int mra_build_stream_wait(mra_build_job* job, int32_t event) {
+  if (!job || event < 0) return MRA_ERR_ARG;
+  std::unique_lock<std::mutex> lk(job->mu);
+  if (event >= 5) {
+    job->cv.wait(lk, [&] { return job->done; });
+    return job->status;
+  }
+  job->cv.wait(lk, [&] { return job->fired > event || job->done; });
+  if (job->fired > event) return MRA_OK;
+  return job->status != MRA_OK ? job->status : MRA_ERR_STATE;
+}
+
+int mra_build_stream_finish(mra_build_job* job, int32_t* n_nodes_out, int32_t* depth_out, int64_t* n_knot_rows_out) {
+  if (!job) return MRA_ERR_ARG;
+  if (job->th.joinable()) job->th.join();
+  const int status = job->status;
+  if (n_nodes_out) *n_nodes_out = job->n_nodes;
+  if (depth_out) *depth_out = job->depth;
+  if (n_knot_rows_out) *n_knot_rows_out = job->n_knot_rows;
+  delete job;
+  return status;
 }
 
 }  // extern "C"

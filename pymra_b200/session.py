@@ -22,11 +22,12 @@ def _dptr(a):
 
 class DeviceSession(object):
     def __init__(self, structure, locs, obs, want_predict=True, device=None, group=None, emulate=None,
-                 gather="all"):
+                 gather="all", staged=None):
         """group: a torch.distributed process group (or True for the default group) to shard whole
         subtrees across its ranks, one GPU per rank (pymra_b200/shard.py); None = single GPU.
         emulate=(world, rank): build the shard of `rank` without a process group; the caller drives
-        likelihood_local_async / likelihood_top_async and reduces `summary` itself (single-GPU tests)."""
+        likelihood_local_async / likelihood_top_async and reduces `summary` itself (single-GPU tests).
+        staged=(dev_locs, dev_obs): torch tensors already holding locs / obs on the device (caller's order)."""
         torch = _torch()
         self.structure = structure
         self.N = structure.N
@@ -69,7 +70,11 @@ class DeviceSession(object):
         aligned = (self.ws.data_ptr() + 255) // 256 * 256
         self.check(self.lib.mra_bind_workspace(self.h, C.c_void_p(aligned), C.c_size_t(self.workspace_bytes)))
         t2 = time.perf_counter()
-        self.upload(locs_c, obs_c)
+        if staged is not None:
+            self.check(self.lib.mra_upload_data_dev(self.h, C.c_void_p(staged[0].data_ptr()),
+                                                    C.c_void_p(staged[1].data_ptr()), self.stream()))
+        else:
+            self.upload(locs_c, obs_c)
         self.timings.update(plan=t1 - t0, alloc_bind=t2 - t1, upload=time.perf_counter() - t2)
 
     # ---- plumbing
@@ -101,6 +106,7 @@ class DeviceSession(object):
             ctype = C.c_int32 if arr.dtype == np.int32 else C.c_int64
             setattr(ms, name, arr.ctypes.data_as(C.POINTER(ctype)))
         self.check(self.lib.mra_set_structure(self.h, C.byref(ms)))
+        self._knot_rows_i64 = keep["knot_rows"]      # no copy when the structure already holds contiguous int64
         self.h2d_structure_bytes = sum(a.nbytes for a in keep.values())
 
     # ---- data / parameters
@@ -133,6 +139,25 @@ class DeviceSession(object):
     def likelihood_top_async(self):
         """Sharded step 3 (after self.summary has been sum-reduced over the ranks): replicated top levels."""
         self.check(self.lib.mra_run_likelihood_top_async(self.h, self.stream(), C.c_void_p(self.summary.data_ptr())))
+
+    # ---- streamed evaluation (overlaps the device passes with a host build that is still drawing knots)
+    def n_parts(self):
+        n = C.c_int32()
+        self.check(self.lib.mra_stream_parts(self.h, C.byref(n)))
+        return int(n.value)
+
+    def _knots_ptr(self):
+        # the int64 array mra_set_structure was given; for a streamed build it is the array the builder fills
+        return self._knot_rows_i64.ctypes.data_as(C.POINTER(C.c_int64))
+
+    def stream_begin(self):
+        self.check(self.lib.mra_stream_begin_async(self.h, self.stream(), self._knots_ptr()))
+
+    def stream_part(self, part):
+        self.check(self.lib.mra_stream_part_async(self.h, self.stream(), int(part), self._knots_ptr()))
+
+    def stream_end(self):
+        self.check(self.lib.mra_stream_end_async(self.h, self.stream()))
 
     def fetch_likelihood(self):
         out = (C.c_double * 2)()

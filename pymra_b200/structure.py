@@ -170,6 +170,91 @@ def build_structure_native(locs, r, M, J, critDepth):
     return st
 
 
+class StreamBuild(object):
+    """Streaming native build (mra_build_stream_* in include/pymra_b200.h): the C++ builder runs on its own
+    thread; `wait(0)` returns once node arrays, permutation and the root's knots are final, `wait(1 + c)` once
+    the knots of the root's child subtree c are, `finish()` joins the build and advances the global NumPy RNG
+    exactly like the reference constructor.  `structure` shares its arrays with the running build."""
+
+    def __init__(self, locs, r, M, J, critDepth):
+        import ctypes as C
+
+        from . import _ffi
+        self._C, self._lib = C, _ffi.lib()
+        self.job = None
+        locs = np.ascontiguousarray(locs, dtype=np.float64)
+        N, d = locs.shape if locs.ndim == 2 else (0, 0)
+        self.state = np.random.get_state()
+        if d != 2 or N >= 2 ** 31 or N < 65536 or M < 1 or M > 12 or self.state[0] != "MT19937":
+            return
+        self._locs = locs
+        self._key = np.ascontiguousarray(self.state[1], dtype=np.uint32).copy()
+        self._pos = C.c_int32(int(self.state[2]))
+        nn = sum(4 ** m for m in range(M + 1))
+        nk = (nn - 4 ** M) * r
+        st = TreeStructure()
+        st.N, st.d, st.r, st.J, st.M, st.depth = N, d, r, J, M, M
+        st.node_level, st.node_parent, st.node_kind = (np.zeros(nn, dtype=np.int32) for _ in range(3))
+        st.node_child_start, st.node_child_count = (np.zeros(nn, dtype=np.int32) for _ in range(2))
+        st.node_row_start, st.node_row_count, st.node_knot_off = (np.zeros(nn, dtype=np.int64) for _ in range(3))
+        st.knot_rows = np.zeros(max(1, nk), dtype=np.int64)[:nk]
+        self._kloc = np.zeros(max(1, nk), dtype=np.int32)[:nk]
+        self._dfs = np.zeros(nn, dtype=np.int32)
+        st.perm = np.empty(N, dtype=np.int64)
+        st.level_off = np.cumsum([0] + [4 ** m for m in range(M + 1)]).astype(np.int32)
+        st.node_id = _LazyIds(st)
+        st.node_kinds_local = _LazyKinds(st, self._kloc)
+        self.structure = st
+        p32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        job = C.c_void_p()
+        rcode = self._lib.mra_build_stream_start(
+            locs.ctypes.data_as(C.POINTER(C.c_double)), N, r, M, J, critDepth,
+            self._key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(self._pos), nn,
+            p32(st.node_level), p32(st.node_parent), p32(st.node_kind), p64(st.node_row_start),
+            p64(st.node_row_count), p32(st.node_child_start), p32(st.node_child_count), p64(st.node_knot_off),
+            p64(st.knot_rows), p32(self._kloc), p64(st.perm), p32(self._dfs), C.byref(job))
+        if rcode == 0:
+            self.job = job
+        elif rcode != 1:
+            raise StructureError("native streaming builder failed with status %d" % rcode)
+
+    @property
+    def started(self):
+        return self.job is not None
+
+    def wait(self, event):
+        """True once `event` has happened; False if the tree turned out to be outside the streaming path
+        (global RNG untouched: the caller falls back to build_structure)."""
+        rcode = self._lib.mra_build_stream_wait(self.job, int(event))
+        if rcode == 1:
+            return False
+        if rcode != 0:
+            raise StructureError("native streaming builder failed with status %d" % rcode)
+        return True
+
+    def finish(self):
+        """Joins the build; on success installs the advanced RNG state.  Returns False for an unsupported tree."""
+        if self.job is None:
+            return False
+        job, self.job = self.job, None
+        rcode = self._lib.mra_build_stream_finish(job, None, None, None)
+        if rcode == 1:
+            return False
+        if rcode != 0:
+            raise StructureError("native streaming builder failed with status %d" % rcode)
+        np.random.set_state((self.state[0], self._key, int(self._pos.value), self.state[3], self.state[4]))
+        return True
+
+    def __del__(self):
+        try:
+            if self.job is not None:
+                job, self.job = self.job, None
+                self._lib.mra_build_stream_finish(job, None, None, None)
+        except Exception:
+            pass
+
+
 class _LazyIds(object):
     def __init__(self, st):
         self._st, self._ids = st, None

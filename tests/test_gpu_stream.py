@@ -1,0 +1,84 @@
+"""Streamed construction (mra_build_stream_* + mra_stream_*): the device passes overlap the host's sequential
+knot draw.  It must give bit-identical results and consume the global RNG exactly like the plain path, which
+the parity tests pin against the reference (tests/test_gpu_parity.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def make(n_side, frac=0.4, seed=3):
+    import pymra_b200.MRATools as mt
+    locs = mt.genLocations2d(n_side)
+    N = len(locs)
+    rng = np.random.RandomState(seed)
+    sel = np.sort(rng.choice(N, int(frac * N), replace=False))
+    y = np.full((N, 1), np.nan)
+    y[sel] = np.sin(5.0 * locs[sel, :1]) + 0.3 * rng.normal(size=(len(sel), 1))
+    return locs, y
+
+
+def construct(locs, y, r, M, stream, monkeypatch, cov=None, crit=-1):
+    import pymra_b200.MRATools as mt
+    from pymra_b200.MRATree import MRATree
+    monkeypatch.setenv("PYMRA_B200_STREAM", "1" if stream else "0")
+    cov = cov or (lambda a, b: mt.Matern32(a, b, l=0.3, sig=1.0))
+    np.random.seed(5)
+    t = MRATree(locs, r, cov, y, 1e-2, M=M, critDepth=crit)
+    state = np.random.get_state()
+    mean, sd = t.predict()
+    return t, float(t.getLikelihood()[0, 0]), np.asarray(mean).ravel().copy(), sd.copy(), state
+
+
+@pytest.mark.parametrize("n_side,r,M,crit", [(300, 16, 3, -1), (300, 16, 4, 1), (700, 32, 5, -1), (2000, 64, 10, -1)])
+def test_streamed_equals_plain(n_side, r, M, crit, monkeypatch):
+    locs, y = make(n_side)
+    tp, lp, mp, sp, statep = construct(locs, y, r, M, False, monkeypatch, crit=crit)
+    assert "streamed" not in tp.timings
+    kp = tp._structure.knot_rows.copy()
+    del tp
+    ts, ls, ms, ss, states = construct(locs, y, r, M, True, monkeypatch, crit=crit)
+    assert ts.timings.get("streamed") == 1.0
+    assert np.array_equal(ts._structure.knot_rows, kp)
+    assert np.array_equal(statep[1], states[1]) and statep[2] == states[2]
+    assert ls == lp
+    assert np.array_equal(ms, mp) and np.array_equal(ss, sp)
+    # frozen-structure re-evaluation after a streamed construction takes the plain device path
+    import pymra_b200.MRATools as mt
+    l2 = float(ts.refit(cov=lambda a, b: mt.Matern32(a, b, l=0.3, sig=1.0))[0, 0])
+    assert l2 == lp
+    m2, s2 = ts.predict()
+    assert np.array_equal(np.asarray(m2).ravel(), mp) and np.array_equal(s2, sp)
+
+
+def test_stream_parts_in_any_order_and_call_order_errors():
+    import pymra_b200.MRATools as mt
+    from pymra_b200 import _ffi
+    from pymra_b200.covariance import introspect
+    from pymra_b200.session import DeviceSession
+    from pymra_b200.structure import build_structure
+    locs, y = make(200)
+    np.random.seed(7)
+    st = build_structure(locs, 16, 3, 4, 9)
+    cov = introspect(lambda a, b: mt.ExpCovFun(a, b, l=0.3), 2)
+    s = DeviceSession(st, locs, y)
+    s.set_params(cov, 1e-2)
+    want = s.likelihood()
+    wm, ws = s.predict()
+    wm, ws = wm.copy(), ws.copy()
+    assert s.n_parts() == 4
+    with pytest.raises(_ffi.MraError):
+        s.stream_part(0)                       # begin first
+    s.stream_begin()
+    for part in (2, 0, 3):
+        s.stream_part(part)
+    with pytest.raises(_ffi.MraError):
+        s.stream_part(3)                       # twice
+    with pytest.raises(_ffi.MraError):
+        s.stream_end()                         # part 1 missing
+    s.stream_part(1)
+    s.stream_end()
+    assert s.fetch_likelihood() == want
+    gm, gs = s.predict()
+    assert np.array_equal(gm, wm) and np.array_equal(gs, ws)
+    s.close()

@@ -90,3 +90,52 @@ def test_threaded_path_on_scattered_points_and_fallback():
     assert build_structure_native(locs, 10, 6, 4, 7) is None
     s1 = np.random.get_state()
     assert np.array_equal(s0[1], s1[1]) and s0[2] == s1[2]
+
+
+@pytest.mark.parametrize("n,r,M,crit", [(300, 8, 3, 9), (300, 8, 3, 1), (400, 16, 4, 0), (512, 32, 5, 9)])
+def test_stream_build_equals_native(n, r, M, crit):
+    """mra_build_stream_*: same arrays and RNG consumption as mra_build_structure_2d, and every event's promise
+    (root knots + permutation at event 0, the knots of subtree c at event 1 + c) holds when it fires."""
+    from pymra_b200.structure import StreamBuild
+    locs = mt.genLocations2d(n)
+    np.random.seed(5)
+    a = build_structure_native(locs, r, M, 4, crit)
+    state_a = np.random.get_state()
+    np.random.seed(5)
+    sb = StreamBuild(locs, r, M, 4, crit)
+    assert sb.started
+    assert sb.wait(0)
+    st = sb.structure
+    assert np.array_equal(st.perm, a.perm)
+    assert np.array_equal(st.node_row_start, a.node_row_start) and np.array_equal(st.node_kind, a.node_kind)
+    assert np.array_equal(st.knot_rows[:r], a.knot_rows[:r])
+    for c in range(4):
+        assert sb.wait(1 + c)
+        for L in range(1, M):
+            lo = int(st.level_off[L]) + c * 4 ** (L - 1)
+            hi = lo + 4 ** (L - 1)
+            assert np.array_equal(st.knot_rows[lo * r:hi * r], a.knot_rows[lo * r:hi * r])
+    assert sb.wait(5)
+    assert sb.finish()
+    state_b = np.random.get_state()
+    same(a, sb.structure)
+    assert np.array_equal(state_a[1], state_b[1]) and state_a[2] == state_b[2]
+
+
+def test_stream_build_refuses_ragged_tree_and_small_inputs():
+    from pymra_b200.structure import StreamBuild
+    np.random.seed(8)
+    before = np.random.get_state()
+    assert not StreamBuild(mt.genLocations2d(100), 8, 2, 4, 9).started          # N < 65536: no job
+    rng = np.random.RandomState(1)
+    locs = rng.uniform(size=(80000, 2))
+    sb = StreamBuild(locs, 10, 6, 4, 7)            # leaves' parents fall under 100 rows (see the test above)
+    assert sb.started
+    assert not all(sb.wait(e) for e in range(6))
+    assert not sb.finish()
+    after = np.random.get_state()
+    assert np.array_equal(before[1], after[1]) and before[2] == after[2]
+    sb = StreamBuild(locs, 10, 5, 4, 6)            # one level less: regular, and equal to the NumPy builder
+    assert sb.started and all(sb.wait(e) for e in range(6)) and sb.finish()
+    np.random.seed(8)
+    same(build_structure(locs, 10, 5, 4, 6, native=False), sb.structure)
