@@ -16,7 +16,9 @@
 #include <algorithm>
 #include <atomic>
 #include <functional>
+#include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -29,6 +31,18 @@
 #endif
 
 namespace {
+
+// MRA_BUILD_TRACE=1: phase timestamps of the threaded build on stderr (seconds since the build started)
+struct Trace {
+  bool on = std::getenv("MRA_BUILD_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what, int k = -1) const {
+    if (!on) return;
+    const double t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (k >= 0) std::fprintf(stderr, "[mra build] %8.4f s  %s %d\n", t, what, k);
+    else std::fprintf(stderr, "[mra build] %8.4f s  %s\n", t, what);
+  }
+};
 
 #if defined(__x86_64__)
 // lane permutation that packs the lanes selected by an 8-bit mask to the high end, first selected lane last
@@ -486,7 +500,7 @@ struct Partitioner {
   std::vector<LevelBits> lv;                 // levels < S: whole-level bit planes
   int S = 0;                                 // levels >= S are partitioned subtree by subtree (4^S subtrees)
   std::vector<std::vector<LevelBits>> sub;   // sub[k][L - S]: bit planes of subtree k at level L
-  std::unique_ptr<std::atomic<int>[]> sub_ready;
+  std::unique_ptr<std::atomic<int>[]> sub_ready;   // sub_ready[k] = number of levels (from S) of subtree k published
   std::atomic<int> ready{0};
   std::atomic<int> failed{0};
   std::atomic<int> all_done{0};              // partition finished (and, in stream mode, the output arrays filled)
@@ -496,6 +510,7 @@ struct Partitioner {
   };
   std::vector<std::vector<PNode>> level_nodes;   // [L][index inside level]: every node's row range
   std::function<void()> on_done;                 // stream mode: fills the caller's node arrays / perm
+  Trace trace;
   static constexpr int64_t BIG = 1 << 18;
 
   // codes and counts of positions [a, b) of a node with means (mx, my)
@@ -654,12 +669,14 @@ struct Partitioner {
       for (size_t i = 0; i < cur.size(); ++i) do_node(cur[i], &next[4 * i], L & 1);
       if (failed.load()) return;
       build_bits(sub[k][L - S], root.s, root.e, 1);
+      sub_ready[k].store(L - S + 1, std::memory_order_release);     // levels S .. L of this subtree are published
       cur.swap(next);
       std::copy(cur.begin(), cur.end(), level_nodes[L + 1].begin() + (size_t)k * cur.size());
     }
   }
 
   void run(double sx0, double sy0) {
+    trace.mark("partition: level-0 arrays ready");
     std::vector<PNode> cur{PNode{0, N, sx0, sy0}}, next;
     level_nodes.assign(M + 1, {});
     for (int L = 0; L <= M; ++L) level_nodes[L].resize((size_t)1 << (2 * L));
@@ -680,6 +697,7 @@ struct Partitioner {
       if (failed.load()) break;
       build_bits(lv[L], 0, N, nthreads);
       ready.store(L + 1, std::memory_order_release);
+      trace.mark("partition: level done", L);
       cur.swap(next);
     }
     const int nsub = (int)sub.size();
@@ -693,16 +711,18 @@ struct Partitioner {
         th.emplace_back([&] {
           for (int k; (k = nextk.fetch_add(1)) < nsub;) {
             if (!failed.load()) run_subtree(k, cur[k]);
-            sub_ready[k].store(1, std::memory_order_release);
+            sub_ready[k].store(M + 1, std::memory_order_release);
           }
         });
       for (auto& t : th) t.join();
+      trace.mark("partition: subtrees done");
     }
     if (failed.load()) {
       ready.store(M + 1, std::memory_order_release);
-      for (int k = 0; k < nsub; ++k) sub_ready[k].store(1, std::memory_order_release);
+      for (int k = 0; k < nsub; ++k) sub_ready[k].store(M + 1, std::memory_order_release);
     } else if (on_done) {
       on_done();
+      trace.mark("partition: output arrays filled");
     }
     all_done.store(1, std::memory_order_release);
   }
@@ -788,6 +808,7 @@ struct RankBuilder {
     }
     int32_t pick[256];
     b.first_r_of_permutation(n_nk, pick);
+    if (level == 0) P->trace.mark("replay: root draws done");
     std::sort(pick, pick + b.r);
     b.rec[me].kind = MRA_NODE_INTERNAL;
     b.rec[me].knot_off = (int64_t)b.kinds_local.size();
@@ -822,7 +843,7 @@ struct RankBuilder {
       lbp = &P->lv[level];
     } else {
       const int64_t k = idx >> (2 * (level - P->S));            // ancestor at level S
-      while (!P->sub_ready[k].load(std::memory_order_acquire)) std::this_thread::yield();
+      while (P->sub_ready[k].load(std::memory_order_acquire) <= level - P->S) std::this_thread::yield();
       lbp = &P->sub[k][level - P->S];
     }
     if (P->failed.load()) {
@@ -856,6 +877,7 @@ struct RankBuilder {
       if (c == 0) b.rec[me].first_child = (int)b.rec.size();
       visit(me, level + 1, 4 * idx + c, off[c], off[c] + cnt[c], levels_left - 1, ckp[c]);
       if (b.status) return;
+      if (level == 0) P->trace.mark("replay: level-1 subtree done", c);
       if (so && level == 0) {          // a level-1 subtree is complete: its knot rows are final
         while (!P->all_done.load(std::memory_order_acquire)) std::this_thread::yield();
         if (P->failed.load()) {
@@ -903,11 +925,46 @@ bool prepare_builder(Builder& B, Pool& pool, int64_t N, int r, int J, int critDe
          B.code && B.slot_of && B.bits;
 }
 
+// worker threads of the partition: all cores but one (the RNG replay keeps the calling thread busy), at most 12;
+// MRA_HOST_THREADS lowers it (several ranks on one host), MRA_BUILD_THREADS sets it outright
+int build_threads() {
+  const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+  int nt = std::max(1, std::min(12, hw - 1));
+  if (hw <= 8) nt = hw;
+  if (const char* e = std::getenv("MRA_HOST_THREADS")) nt = std::max(1, std::min(nt, std::atoi(e)));
+  if (const char* e = std::getenv("MRA_BUILD_THREADS")) nt = std::max(1, std::min(64, std::atoi(e)));
+  return nt;
+}
+
+// level-0 arrays (parallel) and the root's column sums (one thread, sequential: np.mean's order)
+void init_level0(Builder& B, const double* locs, int64_t N, int nthreads, double& sx, double& sy) {
+  std::thread summer([&] {
+    double a = 0.0, b = 0.0;
+    for (int64_t i = 0; i < N; ++i) {
+      a += locs[2 * i];
+      b += locs[2 * i + 1];
+    }
+    sx = a;
+    sy = b;
+  });
+  const int64_t nchunk = std::max(1, nthreads) * 4, step = (N + nchunk - 1) / nchunk;
+  int32_t* R = B.rows[0];
+  double *X = B.xs[0], *Y = B.ys[0];
+  run_parallel(std::max(1, nthreads - 1), nchunk, [&](int64_t k) {
+    const int64_t i0 = k * step, i1 = std::min(N, i0 + step);
+    for (int64_t i = i0; i < i1; ++i) {
+      R[i] = (int32_t)i;
+      X[i] = locs[2 * i];
+      Y[i] = locs[2 * i + 1];
+    }
+  });
+  summer.join();
+}
+
 void setup_partitioner(Partitioner& P, Builder& B, int64_t N, int M) {
   P.N = N;
   P.M = M;
-  P.nthreads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
-  if (const char* e = std::getenv("MRA_HOST_THREADS")) P.nthreads = std::max(1, std::min(P.nthreads, std::atoi(e)));
+  P.nthreads = build_threads();
   for (int b = 0; b < 2; ++b) {
     P.rows[b] = B.rows[b];
     P.xs[b] = B.xs[b];
@@ -1005,14 +1062,7 @@ void stream_body(mra_build_job* job, StreamArgs a) {
       };
       double sx = 0.0, sy = 0.0;
       std::thread worker([&] {
-        for (int64_t i = 0; i < N; ++i) {
-          B.rows[0][i] = (int32_t)i;
-          const double x = a.locs[2 * i], y = a.locs[2 * i + 1];
-          B.xs[0][i] = x;
-          B.ys[0][i] = y;
-          sx += x;
-          sy += y;
-        }
+        init_level0(B, a.locs, N, P.nthreads, sx, sy);
         P.run(sx, sy);
       });
       RankBuilder RB{&B, &P, M, &so};
@@ -1056,18 +1106,8 @@ int mra_build_structure_2d(const double* locs, int64_t n_locs, int32_t r, int32_
   if (!prepare_builder(B, pool, n_locs, r, J, critDepth, mt_key, *mt_pos)) return MRA_ERR_NOMEM;
   const int64_t N = n_locs;
   double sx = 0.0, sy = 0.0;
-  // level-0 arrays and the root's column sums (sequential, np.mean's order)
-  auto init_level0 = [&] {
-    sx = sy = 0.0;
-    for (int64_t i = 0; i < N; ++i) {
-      B.rows[0][i] = (int32_t)i;
-      const double x = locs[2 * i], y = locs[2 * i + 1];
-      B.xs[0][i] = x;
-      B.ys[0][i] = y;
-      sx += x;
-      sy += y;
-    }
-  };
+  const int nthreads0 = build_threads();
+  auto init_level0 = [&] { ::init_level0(B, locs, N, nthreads0, sx, sy); };
   bool done = false;
   if (M >= 1 && N >= (int64_t)1 << 16) {
     // threaded two-phase build; falls back to the serial DFS below when the tree is not regular

@@ -14,7 +14,7 @@ int main(){
   std::vector<int32_t> lvl(max_nodes),par(max_nodes),kind(max_nodes),cst(max_nodes),ccnt(max_nodes),dfs(max_nodes),kloc((size_t)max_nodes*r);
   std::vector<int64_t> rs(max_nodes),rc(max_nodes),koff(max_nodes),knots((size_t)max_nodes*r),perm(N);
   int nn,depth; int64_t nk;
-  for(int rep=0;rep<12;++rep){
+  for(int rep=0;rep<6;++rep){
   auto t0=std::chrono::steady_clock::now();
   int rcode=mra_build_structure_2d(locs.data(),N,r,M,J,cd,key.data(),&pos,max_nodes,&nn,&depth,lvl.data(),par.data(),kind.data(),rs.data(),rc.data(),cst.data(),ccnt.data(),koff.data(),knots.data(),kloc.data(),&nk,perm.data(),dfs.data());
   auto t1=std::chrono::steady_clock::now();
