@@ -118,10 +118,26 @@ class MRATree(object):
             self._construct_streamed(locs_c, obs_arr, r, M, J, critDepth, device)
         if self._session is None:
             t1 = time.perf_counter()
-            self._structure = build_structure(locs_c, r, M, J, critDepth)
+            staged = None
+            if group is not None:
+                # one build per group (rank 0 draws, everybody receives); the inputs go to the device meanwhile
+                from .shard import build_structure_group
+                box = []
+
+                def early_h2d():
+                    import torch
+                    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+                    box.append((torch.from_numpy(locs_c).to(dev, non_blocking=True),
+                                torch.from_numpy(np.ascontiguousarray(obs_arr).reshape(-1)).to(dev, non_blocking=True)))
+                self._structure = build_structure_group(locs_c, r, M, J, critDepth, None if group is True else group,
+                                                        async_start=early_h2d)
+                staged = box[0] if box else None
+            else:
+                self._structure = build_structure(locs_c, r, M, J, critDepth)
             t2 = time.perf_counter()
             self._session = DeviceSession(self._structure, locs_c, obs_arr, want_predict=True, device=device,
-                                          group=group, gather=gather)
+                                          group=group, gather=gather, staged=staged)
+            del staged
             t3 = time.perf_counter()
             self._mom = None
             self._evaluate()

@@ -69,3 +69,103 @@ def owned_rows(st, role):
             a = int(st.node_row_start[n])
             mask[a:a + int(st.node_row_count[n])] = True
     return mask
+
+
+# ---- one build per group: rank 0 draws the knots, everybody receives the tree --------------------------------
+_I32_FIELDS = ("node_level", "node_parent", "node_kind", "node_child_start", "node_child_count",
+               "node_row_start", "node_row_count", "node_knot_off")
+
+
+def build_structure_group(locs, r, M, J, critDepth, group=None, async_start=None):
+    """The tree for a process group.  The reference's knot draws are one sequential legacy-RNG stream
+    (pyMRA/MRANode.py:191-193 in DFS pre-order), so N ranks building redundantly only fight for the host's
+    memory bandwidth.  Instead group rank 0 runs the native builder with all the host threads and broadcasts
+    the flat arrays (about 7 bytes per location) together with the advanced MT19937 state, which every rank
+    installs -- afterwards all ranks hold the same tree and the same global NumPy RNG state, exactly as if
+    each had built it.  Trees outside the native builder's path (small / 1-D / ragged) are built by every
+    rank on its own as before.  Works over NCCL (device tensors) and gloo (host tensors).
+    async_start: optional callable run on every rank while rank 0 builds (e.g. the H2D copy of the inputs)."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    from .structure import StreamBuild, TreeStructure, _LazyIds, _LazyKinds, build_structure, build_structure_native
+    rank = dist.get_rank(group)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    locs = np.ascontiguousarray(locs, dtype=np.float64)
+    N = len(locs)
+    header = torch.zeros(8, dtype=torch.int64)
+    st = None
+    if rank == 0:
+        saved = {k: os.environ.get(k) for k in ("MRA_BUILD_THREADS",)}
+        ncpu = os.cpu_count() or 8
+        os.environ["MRA_BUILD_THREADS"] = str(ncpu if ncpu <= 8 else min(12, ncpu - 1))   # the other ranks wait
+        try:
+            sb = StreamBuild(locs, r, M, J, critDepth) if locs.ndim == 2 and locs.shape[1] == 2 else None
+            if async_start is not None:
+                async_start()
+            if sb is not None and sb.started and sb.wait(5) and sb.finish():
+                st = sb.structure
+            else:
+                if sb is not None:
+                    sb.finish()
+                st = build_structure_native(locs, r, M, J, critDepth) if locs.ndim == 2 and locs.shape[1] == 2 else None
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        if st is not None:
+            state = np.random.get_state()
+            header[:6] = torch.tensor([1, st.n_nodes, st.depth, len(st.knot_rows), int(state[2]), N])
+    elif async_start is not None:
+        async_start()
+    header = header.to(dev)
+    dist.broadcast(header, src=src, group=group)
+    if on_gpu and rank != 0:                # sleep, do not spin, while rank 0 is still building
+        ev = torch.cuda.Event(blocking=True)
+        ev.record()
+        ev.synchronize()
+    header = header.cpu()
+    if int(header[0]) == 0:                 # not a native tree: every rank builds it (RNG untouched so far)
+        return build_structure(locs, r, M, J, critDepth)
+    nn, depth, nk, mt_pos = int(header[1]), int(header[2]), int(header[3]), int(header[4])
+    total = N + len(_I32_FIELDS) * nn + 2 * nk + 624
+    if rank == 0:
+        kloc = st.node_kinds_local._kloc
+        parts = [st.perm.astype(np.int32)] + [np.asarray(getattr(st, f)).astype(np.int32) for f in _I32_FIELDS]
+        parts += [st.knot_rows.astype(np.int32), np.asarray(kloc, dtype=np.int32),
+                  np.ascontiguousarray(state[1], dtype=np.uint32).view(np.int32)]
+        payload = torch.from_numpy(np.concatenate(parts)).to(dev)
+    else:
+        payload = torch.empty(total, dtype=torch.int32, device=dev)
+    dist.broadcast(payload, src=src, group=group)
+    if rank == 0:
+        return st
+    buf = payload.cpu().numpy()
+    o = 0
+
+    def take(n):
+        nonlocal o
+        a = buf[o:o + n]
+        o += n
+        return a
+    st = TreeStructure()
+    st.N, st.d, st.r, st.J, st.M, st.depth = N, locs.shape[1], r, J, M, depth
+    st.perm = take(N).astype(np.int64)
+    for f in _I32_FIELDS:
+        a = take(nn)
+        setattr(st, f, a.astype(np.int64) if f in ("node_row_start", "node_row_count", "node_knot_off") else a.copy())
+    st.knot_rows = take(nk).astype(np.int64)
+    kloc = take(nk).copy()
+    key = take(624).view(np.uint32).copy()
+    st.level_off = np.searchsorted(st.node_level, np.arange(depth + 2)).astype(np.int32)
+    st.node_id = _LazyIds(st)
+    st.node_kinds_local = _LazyKinds(st, kloc)
+    mine = np.random.get_state()
+    np.random.set_state((mine[0], key, mt_pos, mine[3], mine[4]))
+    return st

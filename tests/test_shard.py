@@ -93,3 +93,53 @@ def test_gloo_sharded_model_matches_unsharded(name, world):
         assert np.max(np.abs(sd - ref["sd"])) <= 1e-10
     # and the reference itself
     assert abs(got[0][2] - float(g["lik"])) <= 1e-9 * abs(float(g["lik"]))
+
+
+def _group_build_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import pymra_b200.MRATools as mt
+    from pymra_b200.shard import build_structure_group
+    from pymra_b200.structure import build_structure
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = []
+    # streamed native build (N >= 65536), plain native build, and a tree outside the native path (KMeans nodes)
+    for n, r, M, crit in [(300, 16, 4, -1), (300, 16, 4, 1), (60, 8, 2, -1), (12, 4, 2, -1)]:
+        locs = mt.genLocations2d(n)
+        crit = M + 1 if crit < 0 else crit
+        np.random.seed(21)
+        want = build_structure(locs, r, M, 4, crit)
+        want_state = np.random.get_state()
+        native_tree = n >= 60
+        # a native tree is rank 0's (only its RNG state matters); otherwise every rank builds from its own state,
+        # which callers keep identical across ranks
+        np.random.seed(21 if rank == 0 or not native_tree else 99)
+        called = []
+        got = build_structure_group(locs, r, M, 4, crit, async_start=lambda: called.append(1))
+        got_state = np.random.get_state()
+        same = all(np.array_equal(getattr(want, f), getattr(got, f)) for f in
+                   ("perm", "node_level", "node_parent", "node_kind", "node_row_start", "node_row_count",
+                    "node_child_start", "node_child_count", "node_knot_off", "knot_rows", "level_off"))
+        same = same and all(np.array_equal(want.node_kinds_local[k], got.node_kinds_local[k]) for k in (0, 1, want.n_nodes - 1))
+        same = same and np.array_equal(want_state[1], got_state[1]) and want_state[2] == got_state[2]
+        ok.append(bool(same) and called == [1])
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_group_build_broadcasts_rank0_tree_and_rng_state():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_group_build_worker, args=(rk, 2, port, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok in got:
+        assert ok == [True, True, True, True], (rank, ok)
