@@ -318,7 +318,8 @@ def run_ours(args, rank, world, local_rank):
                     "what": "MRATree(locs, r, cov, obs, R, M) + getLikelihood() + predict(), host numpy in/out, "
                             "fresh knot draw per construction (reference RNG semantics)"
                             + ("; streamed: device passes overlap the host knot draw" if e2e_breakdown.get("streamed") else ""),
-                    "likelihood": lik_e2e, "host_breakdown_s": e2e_breakdown},
+                    "likelihood": lik_e2e, "host_breakdown_s": e2e_breakdown,
+                    "step_s": [round(t, 4) for t in t_e2e]},
             "gpu_launches": int(launches * args.steps * world),
             "roofline": roofline, "kernels": kern, "cpu_baseline": cb, "clocks": clocks,
             "algorithmic_flops": {"likelihood": f_lik, "predict": f_pred},
@@ -336,7 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
