@@ -114,8 +114,8 @@ class MRATree(object):
         t1 = time.perf_counter()
         self.timings["args_and_cov"] = t1 - t0
         self._session = None
-        if group is None and self.d == 2 and os.environ.get("PYMRA_B200_STREAM", "1") != "0":
-            self._construct_streamed(locs_c, obs_arr, r, M, J, critDepth, device)
+        if self.d == 2 and os.environ.get("PYMRA_B200_STREAM", "1") != "0":
+            self._construct_streamed(locs_c, obs_arr, r, M, J, critDepth, device, group, gather)
         if self._session is None:
             t1 = time.perf_counter()
             staged = None
@@ -146,17 +146,29 @@ class MRATree(object):
                                 **self._session.timings)
         self.root = _Root(self)
 
-    def _construct_streamed(self, locs_c, obs_arr, r, M, J, critDepth, device):
-        """Large regular 2-D trees on one GPU: the C++ builder runs on its own thread (StreamBuild) and the
-        device passes start as soon as the RNG-independent part of the tree (partition, permutation, the
-        root's knots) is known; each subtree of the root is evaluated when the sequential knot draw
-        (MRANode.py:191-193, DFS pre-order) has left it.  Same results and RNG consumption as the plain path;
-        leaves self._session = None (global RNG untouched) when the tree is outside this path."""
+    def _construct_streamed(self, locs_c, obs_arr, r, M, J, critDepth, device, group=None, gather="all"):
+        """Large regular 2-D trees: the C++ builder runs on its own thread (StreamBuild) and the device passes
+        start as soon as the RNG-independent part of the tree (partition, permutation, the root's knots) is
+        known; each subtree of the root is evaluated when the sequential knot draw (MRANode.py:191-193, DFS
+        pre-order) has left it.  With a process group of 2-4 ranks (sharded at level 1, so the root's subtrees
+        ARE the shards) rank 0 builds and forwards every event (GroupStreamBuild) and each rank evaluates the
+        subtrees it owns.  Same results and RNG consumption as the plain path; leaves self._session = None
+        (global RNG untouched) when the tree is outside this path."""
         import torch
         if not torch.cuda.is_available():
             return                      # the plain path raises the "no CPU fallback" error
         t0 = time.perf_counter()
-        sb = StreamBuild(locs_c, r, M, J, critDepth)
+        if group is None:
+            sb = StreamBuild(locs_c, r, M, J, critDepth)
+            world, rank = 1, 0
+        else:
+            import torch.distributed as dist
+            from .shard import GroupStreamBuild
+            g = None if group is True else group
+            world, rank = dist.get_world_size(g), dist.get_rank(g)
+            if world > 4 or len(locs_c) < 65536 or M < 1 or M > 12:     # deterministic on every rank
+                return
+            sb = GroupStreamBuild(locs_c, r, M, J, critDepth, g)
         if not sb.started:
             return
         session = None
@@ -165,40 +177,46 @@ class MRATree(object):
             dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
             staged = (torch.from_numpy(locs_c).to(dev), torch.from_numpy(np.ascontiguousarray(obs_arr).reshape(-1)).to(dev))
             t1 = time.perf_counter()
-            if not sb.wait(0):
-                return
+            ok = sb.wait(0)
             t2 = time.perf_counter()
-            session = DeviceSession(sb.structure, locs_c, obs_arr, want_predict=True, device=device, staged=staged)
+            nparts = 0
+            if ok:
+                session = DeviceSession(sb.structure, locs_c, obs_arr, want_predict=True, device=device, group=group,
+                                        gather=gather, staged=staged)
+                session.set_params(self._cov, self._R)
+                nparts = session.n_parts()
             del staged
-            session.set_params(self._cov, self._R)
             t3 = time.perf_counter()
-            nparts = session.n_parts()
-            if nparts != 4:
-                return
-            session.stream_begin()
+            streamable = ok and nparts == 4 and session.shard_level == (0 if world == 1 else 1)
+            if streamable:
+                session.stream_begin()
             waits = 0.0
-            for c in range(nparts):
+            for c in range(4):                       # every rank follows every event (they are collective)
                 tw = time.perf_counter()
-                if not sb.wait(1 + c):
-                    return
+                ok = sb.wait(1 + c) and ok
                 waits += time.perf_counter() - tw
-                session.stream_part(c)
+                if ok and streamable and c % world == rank:
+                    session.stream_part(c)
             tw = time.perf_counter()
-            if not sb.finish():
-                return
+            ok = sb.finish() and ok
             waits += time.perf_counter() - tw
-            session.stream_end()
+            if not ok:
+                return
+            if streamable:
+                session.stream_end()
+            else:                         # built (RNG advanced) but not streamable: plain passes on the finished tree
+                session.likelihood_async()
             self._structure = sb.structure
             self._session, session = session, None
             self._d, self._u = self._session.fetch_likelihood()
             self._mom = None
             t4 = time.perf_counter()
             self.timings.update(structure=t2 - t0, early_h2d=t1 - t0, session_plan_upload=t3 - t2,
-                                likelihood=t4 - t3, build_waits_in_likelihood=waits, streamed=1.0,
+                                likelihood=t4 - t3, build_waits_in_likelihood=waits,
+                                streamed=1.0 if streamable else 0.0,
                                 **self._session.timings)
         finally:
             if session is not None:       # fell out of the streaming path after device work had started
-                import torch
                 torch.cuda.synchronize()
                 session.close()
             sb.finish()

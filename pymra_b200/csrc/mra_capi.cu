@@ -68,6 +68,7 @@ struct mra_handle {
   std::vector<std::vector<Range>> part_leaves;              // [part] -> ranges of `leaves`
   std::vector<std::vector<Range>> part_knots;               // [part] -> ranges of knot_rows
   int stream_parts_done = 0;                                // bit mask of the parts run since mra_stream_begin_async
+  int my_parts = 0;                                         // bit mask of the parts this rank evaluates (all when unsharded)
   bool stream_open = false, leafq_done = false;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_event = nullptr;
@@ -377,12 +378,23 @@ int reset_pass(mra_handle* h, cudaStream_t st) {
   return MRA_OK;
 }
 
+// sharded: the summaries (A~_c, d_c) of this rank's subtree roots into its slots of dev_summary
+int export_summaries(mra_handle* h, cudaStream_t st, const DevCtx& c, double* dev_summary) {
+  if (h->shard_level <= 0 || h->sroots.empty()) return MRA_OK;
+  const Layout& L = h->lay;
+  const int r = h->r;
+  const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->sroots_off);
+  const int W = h->shard_level * r + 1, nb = (W - 1 + TB - 1) / TB;
+  const int nt = nb * (nb + 1) / 2 + (W + TB - 1) / TB;
+  MRA_FOR_VEC(h, LAUNCH("export_summary", k_assemble_A<V_><<<(unsigned)((h->sroots.size() + 15) / 16 * 16) * nt, NT, smem_plain(), st>>>(
+                                              c, list, dev_summary, h->slot_base, (int)h->sroots.size(), nt)));
+  return MRA_OK;
+}
+
 // Prior pass, leaf terms and the upward pass down to the shard level (level 0 when not sharded).
 // Sharded: ends by exporting the summaries of this rank's subtree roots into dev_summary.
 int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary) {
-  const Layout& L = h->lay;
   DevCtx c = make_ctx(h);
-  const int r = h->r;
   int rc = reset_pass(h, st);
   if (rc) return rc;
   // ---- prior, top-down
@@ -398,13 +410,8 @@ int launch_likelihood_local(mra_handle* h, cudaStream_t st, double* dev_summary)
     rc = upward_level(h, st, c, m);
     if (rc) return rc;
   }
-  if (h->shard_level > 0 && !h->sroots.empty()) {
-    const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->sroots_off);
-    const int W = h->shard_level * r + 1, nb = (W - 1 + TB - 1) / TB;
-    const int nt = nb * (nb + 1) / 2 + (W + TB - 1) / TB;
-    MRA_FOR_VEC(h, LAUNCH("export_summary", k_assemble_A<V_><<<(unsigned)((h->sroots.size() + 15) / 16 * 16) * nt, NT, smem_plain(), st>>>(
-                                                c, list, dev_summary, h->slot_base, (int)h->sroots.size(), nt)));
-  }
+  rc = export_summaries(h, st, c, dev_summary);
+  if (rc) return rc;
   CU(cudaGetLastError());
   return MRA_OK;
 }
@@ -549,7 +556,7 @@ void build_lists(mra_handle* h) {
   h->part_tiles.clear();
   h->part_leaves.clear();
   h->part_knots.clear();
-  if (s == 0 && nn > 1 && h->kind[0] == KIND_INTERNAL && !h->internal_at.empty()) {
+  if (s <= 1 && nn > 1 && h->kind[0] == KIND_INTERNAL && !h->internal_at.empty()) {
     const int np = h->child_count[0], c0 = h->child_start[0];
     std::vector<int> part_of((size_t)nn, -1);
     for (int n = 1; n < nn; ++n) part_of[n] = h->parent[n] == 0 ? n - c0 : part_of[h->parent[n]];
@@ -589,7 +596,14 @@ void build_lists(mra_handle* h) {
       if (!lr.empty() && lr.back().begin + lr.back().count == i) ++lr.back().count;
       else lr.push_back(Range{i, 1});
     }
-    if (!ok) h->n_parts = 0;      // cannot happen with level-by-level numbering; streaming is refused then
+    if (np > 30) ok = false;
+    h->my_parts = 0;
+    for (int pp = 0; pp < np && ok; ++pp) {
+      const int child = c0 + pp;
+      if (s == 0 || h->role[child] == 1) h->my_parts |= 1 << pp;
+      else if (h->role[child] != 0) ok = false;          // a replicated leaf child of the root: not streamed
+    }
+    if (!ok) h->n_parts = 0;      // streaming is refused then
   }
 }
 
@@ -1121,7 +1135,7 @@ int mra_run_likelihood_top_async(mra_handle* h, void* stream, const double* dev_
 
 int mra_stream_parts(const mra_handle* h, int32_t* n_parts) {
   if (!h || !n_parts) return MRA_ERR_ARG;
-  *n_parts = h->shard_level == 0 ? h->n_parts : 0;
+  *n_parts = h->shard_level <= 1 ? h->n_parts : 0;
   return MRA_OK;
 }
 
@@ -1147,7 +1161,8 @@ static int upload_knot_ranges(mra_handle* h, cudaStream_t st, const int64_t* kno
 
 int mra_stream_begin_async(mra_handle* h, void* stream, const int64_t* knot_rows) {
   if (!h) return MRA_ERR_ARG;
-  if (h->shard_level > 0 || h->n_parts <= 0) return fail(h, MRA_ERR_STATE, "streamed evaluation needs an unsharded tree with an internal root");
+  if (h->shard_level > 1 || h->n_parts <= 0)
+    return fail(h, MRA_ERR_STATE, "streamed evaluation needs an internal root and a handle that is unsharded or sharded at level 1");
   int rc = ready_to_run(h);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1170,6 +1185,7 @@ int mra_stream_part_async(mra_handle* h, void* stream, int32_t part, const int64
   if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
   if (part < 0 || part >= h->n_parts) return fail(h, MRA_ERR_ARG, "part out of range");
   if (h->stream_parts_done & (1 << part)) return fail(h, MRA_ERR_STATE, "part already evaluated");
+  if (!(h->my_parts & (1 << part))) return fail(h, MRA_ERR_ARG, "this part belongs to another rank");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CU(cudaSetDevice(h->device));
   DevCtx c = make_ctx(h);
@@ -1199,8 +1215,9 @@ int mra_stream_part_async(mra_handle* h, void* stream, int32_t part, const int64
 
 int mra_stream_end_async(mra_handle* h, void* stream) {
   if (!h) return MRA_ERR_ARG;
+  if (h->shard_level > 0) return fail(h, MRA_ERR_STATE, "sharded handle: use mra_stream_end_local_async + mra_run_likelihood_top_async");
   if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
-  if (h->stream_parts_done != (1 << h->n_parts) - 1) return fail(h, MRA_ERR_STATE, "not every part has been evaluated");
+  if (h->stream_parts_done != h->my_parts) return fail(h, MRA_ERR_STATE, "not every part has been evaluated");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CU(cudaSetDevice(h->device));
   DevCtx c = make_ctx(h);
@@ -1209,6 +1226,23 @@ int mra_stream_end_async(mra_handle* h, void* stream) {
   h->stream_open = false;
   h->leafq_done = h->want_predict;
   return launch_likelihood_top(h, st, nullptr);     // shard_level == 0: only the final reduction
+}
+
+int mra_stream_end_local_async(mra_handle* h, void* stream, double* dev_summary) {
+  if (!h) return MRA_ERR_ARG;
+  if (h->shard_level != 1) return fail(h, MRA_ERR_STATE, "mra_stream_end_local_async is for handles sharded at level 1");
+  if (!dev_summary) return fail(h, MRA_ERR_ARG, "sharded handle needs a summary buffer");
+  if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
+  if (h->stream_parts_done != h->my_parts) return fail(h, MRA_ERR_STATE, "not every part of this rank has been evaluated");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  DevCtx c = make_ctx(h);
+  int rc = export_summaries(h, st, c, dev_summary);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  h->stream_open = false;
+  h->leafq_done = h->want_predict;
+  return MRA_OK;
 }
 
 int mra_fetch_likelihood(mra_handle* h, void* stream, double out[2]) {

@@ -151,13 +151,25 @@ class DeviceSession(object):
         return self._knot_rows_i64.ctypes.data_as(C.POINTER(C.c_int64))
 
     def stream_begin(self):
+        if self.shard_level:
+            self.summary.zero_()
         self.check(self.lib.mra_stream_begin_async(self.h, self.stream(), self._knots_ptr()))
 
     def stream_part(self, part):
         self.check(self.lib.mra_stream_part_async(self.h, self.stream(), int(part), self._knots_ptr()))
 
+    def stream_end_local(self):
+        """Sharded at level 1: my summaries into self.summary (the caller reduces them, then likelihood_top_async)."""
+        self.check(self.lib.mra_stream_end_local_async(self.h, self.stream(), C.c_void_p(self.summary.data_ptr())))
+
     def stream_end(self):
-        self.check(self.lib.mra_stream_end_async(self.h, self.stream()))
+        if not self.shard_level:
+            self.check(self.lib.mra_stream_end_async(self.h, self.stream()))
+            return
+        import torch.distributed as dist
+        self.stream_end_local()
+        dist.all_reduce(self.summary, group=self.group)       # disjoint slots: the sum is exact
+        self.likelihood_top_async()
 
     def fetch_likelihood(self):
         out = (C.c_double * 2)()

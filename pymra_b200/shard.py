@@ -169,3 +169,164 @@ def build_structure_group(locs, r, M, J, critDepth, group=None, async_start=None
     mine = np.random.get_state()
     np.random.set_state((mine[0], key, mt_pos, mine[3], mine[4]))
     return st
+
+
+class GroupStreamBuild(object):
+    """StreamBuild (pymra_b200/structure.py) for a process group: rank 0 runs the streaming native builder and
+    forwards every progress event with the arrays that became final -- event 0: permutation, node table and the
+    root's knots; event 1 + c: the knots of the root's child subtree c; event 5: the advanced MT19937 state.
+    Every rank sees the same `wait(event)` / `finish()` results and ends with the same tree and global NumPy RNG
+    state.  Broadcasts run on their own high-priority stream so that they never queue behind the evaluation
+    kernels of a rank that is still busy with an earlier subtree."""
+
+    def __init__(self, locs, r, M, J, critDepth, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from .structure import StreamBuild
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group)
+        self.src = dist.get_global_rank(group, 0) if group is not None else 0
+        self.on_gpu = dist.get_backend(group) == "nccl"
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if self.on_gpu else torch.device("cpu")
+        self.comm = torch.cuda.Stream(priority=-1) if self.on_gpu else None
+        self.locs = np.ascontiguousarray(locs, dtype=np.float64)
+        self.r, self.M, self.J = r, M, J
+        self.sb = None
+        self.done = None
+        self.structure = None
+        ok = 0
+        if self.rank == 0:
+            import os
+            ncpu = os.cpu_count() or 8
+            saved = os.environ.get("MRA_BUILD_THREADS")
+            os.environ["MRA_BUILD_THREADS"] = str(ncpu if ncpu <= 8 else min(12, ncpu - 1))   # the other ranks wait
+            try:
+                if self.locs.ndim == 2 and self.locs.shape[1] == 2:
+                    self.sb = StreamBuild(self.locs, r, M, J, critDepth)
+            finally:
+                if saved is None:
+                    os.environ.pop("MRA_BUILD_THREADS", None)
+                else:
+                    os.environ["MRA_BUILD_THREADS"] = saved
+            ok = 1 if (self.sb is not None and self.sb.started) else 0
+        head = self._bcast(np.array([ok], dtype=np.int32), 1)
+        self.started = bool(head[0])
+        self.N = len(self.locs)
+        self.nn = sum(4 ** m for m in range(M + 1))
+        self.nk = (self.nn - 4 ** M) * r
+        self.level_off = np.cumsum([0] + [4 ** m for m in range(M + 1)]).astype(np.int64)
+
+    # one int32 payload from rank 0 to everybody; non-root ranks sleep (not spin) while rank 0 is busy
+    def _bcast(self, arr, n):
+        torch, dist = self.torch, self.dist
+        if self.rank == 0:
+            t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32))
+        else:
+            t = torch.empty(n, dtype=torch.int32)
+        if not self.on_gpu:
+            dist.broadcast(t, src=self.src, group=self.group)
+            return t.numpy()
+        with torch.cuda.stream(self.comm):
+            t = t.to(self.dev, non_blocking=True)
+            dist.broadcast(t, src=self.src, group=self.group)
+            if self.rank == 0:
+                return arr
+            ev = torch.cuda.Event(blocking=True)
+            ev.record(self.comm)
+            ev.synchronize()
+            return t.cpu().numpy()
+
+    def _subtree_slots(self, c):
+        r = self.r
+        out = []
+        for L in range(1, self.M):
+            lo = int(self.level_off[L]) + c * 4 ** (L - 1)
+            out.append((lo * r, (lo + 4 ** (L - 1)) * r))
+        return out
+
+    def wait(self, event):
+        from .structure import TreeStructure, _LazyIds, _LazyKinds
+        rank0 = self.rank == 0
+        r, nn, nk, N = self.r, self.nn, self.nk, self.N
+        if event == 0:
+            size = 1 + N + len(_I32_FIELDS) * nn + 2 * r
+            msg = None
+            if rank0:
+                ok = self.sb.wait(0)
+                st = self.sb.structure
+                if ok:
+                    msg = np.concatenate([np.array([1], dtype=np.int32), st.perm.astype(np.int32)]
+                                         + [np.asarray(getattr(st, f)).astype(np.int32) for f in _I32_FIELDS]
+                                         + [st.knot_rows[:r].astype(np.int32), self.sb._kloc[:r]])
+                else:
+                    msg = np.zeros(size, dtype=np.int32)
+            msg = self._bcast(msg, size)
+            if not msg[0]:
+                return False
+            if rank0:
+                self.structure = self.sb.structure
+                return True
+            o = 1
+            st = TreeStructure()
+            st.N, st.d, st.r, st.J, st.M, st.depth = N, 2, r, self.J, self.M, self.M
+            st.perm = msg[o:o + N].astype(np.int64)
+            o += N
+            for f in _I32_FIELDS:
+                a = msg[o:o + nn]
+                o += nn
+                setattr(st, f, a.astype(np.int64) if f in ("node_row_start", "node_row_count", "node_knot_off") else a.copy())
+            st.knot_rows = np.zeros(max(1, nk), dtype=np.int64)[:nk]
+            self._kloc = np.zeros(max(1, nk), dtype=np.int32)[:nk]
+            st.knot_rows[:r] = msg[o:o + r]
+            self._kloc[:r] = msg[o + r:o + 2 * r]
+            st.level_off = self.level_off.astype(np.int32)
+            st.node_id = _LazyIds(st)
+            st.node_kinds_local = _LazyKinds(st, self._kloc)
+            self.structure = st
+            return True
+        if 1 <= event <= 4:
+            slots = self._subtree_slots(event - 1)
+            cnt = sum(b - a for a, b in slots)
+            msg = None
+            if rank0:
+                ok = self.sb.wait(event)
+                st = self.sb.structure
+                if ok:
+                    msg = np.concatenate([np.array([1], dtype=np.int32)]
+                                         + [st.knot_rows[a:b].astype(np.int32) for a, b in slots]
+                                         + [self.sb._kloc[a:b] for a, b in slots])
+                else:
+                    msg = np.zeros(1 + 2 * cnt, dtype=np.int32)
+            msg = self._bcast(msg, 1 + 2 * cnt)
+            if not msg[0]:
+                return False
+            if not rank0:
+                o = 1
+                for a, b in slots:
+                    self.structure.knot_rows[a:b] = msg[o:o + b - a]
+                    o += b - a
+                for a, b in slots:
+                    self._kloc[a:b] = msg[o:o + b - a]
+                    o += b - a
+            return True
+        return self.finish()
+
+    def finish(self):
+        if self.done is not None:
+            return self.done
+        if not self.started:
+            self.done = False
+            return False
+        msg = None
+        if self.rank == 0:
+            ok = self.sb.finish()
+            state = np.random.get_state()
+            msg = np.concatenate([np.array([1 if ok else 0, int(state[2])], dtype=np.int32),
+                                  np.ascontiguousarray(state[1], dtype=np.uint32).view(np.int32)])
+        msg = self._bcast(msg, 2 + 624)
+        self.done = bool(msg[0])
+        if self.done and self.rank != 0:
+            mine = np.random.get_state()
+            np.random.set_state((mine[0], msg[2:].view(np.uint32).copy(), int(msg[1]), mine[3], mine[4]))
+        return self.done

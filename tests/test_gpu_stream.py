@@ -82,3 +82,58 @@ def test_stream_parts_in_any_order_and_call_order_errors():
     gm, gs = s.predict()
     assert np.array_equal(gm, wm) and np.array_equal(gs, ws)
     s.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_emulated_level1_shards_stream_their_parts(world):
+    """Handles sharded at level 1 (2-4 GPUs) stream the parts they own: same summaries, likelihood and
+    predictions as the plain sharded pass; another rank's part is refused."""
+    import torch
+    import pymra_b200.MRATools as mt
+    from pymra_b200 import _ffi
+    from pymra_b200.covariance import introspect
+    from pymra_b200.session import DeviceSession
+    from pymra_b200.structure import build_structure
+    locs, y = make(200)
+    np.random.seed(7)
+    st = build_structure(locs, 16, 3, 4, 9)
+    cov = introspect(lambda a, b: mt.Matern32(a, b, l=0.3, sig=1.0), 2)
+    N = st.N
+    sess = []
+    for rank in range(world):
+        s = DeviceSession(st, locs, y, want_predict=True, emulate=(world, rank))
+        s.set_params(cov, 1e-2)
+        assert s.shard_level == 1 and s.n_parts() == 4
+        sess.append(s)
+
+    def finish(total):
+        liks, mean, sd = [], torch.zeros(N, dtype=torch.float64, device="cuda"), torch.zeros(N, dtype=torch.float64, device="cuda")
+        for s in sess:
+            s.summary.copy_(total)
+            s.likelihood_top_async()
+            liks.append(s.fetch_likelihood())
+            m_k, s_k = torch.empty_like(mean), torch.empty_like(sd)
+            s.predict_dev(m_k, s_k)
+            mean += m_k
+            sd += s_k
+        return liks, mean.cpu().numpy(), sd.cpu().numpy()
+
+    for s in sess:
+        s.likelihood_local_async()
+    want_total = torch.stack([s.summary for s in sess]).sum(0)
+    want = finish(want_total.clone())
+    for rank, s in enumerate(sess):
+        s.stream_begin()
+        with pytest.raises(_ffi.MraError):
+            s.stream_part((rank + 1) % world)              # owned by the next rank (round-robin)
+        for part in reversed(range(4)):
+            if part % world == rank:
+                s.stream_part(part)
+        s.stream_end_local()
+    got_total = torch.stack([s.summary for s in sess]).sum(0)
+    assert torch.equal(got_total, want_total)
+    got = finish(got_total)
+    assert got[0] == want[0] and all(l == got[0][0] for l in got[0])
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    for s in sess:
+        s.close()

@@ -143,3 +143,66 @@ def test_gloo_group_build_broadcasts_rank0_tree_and_rng_state():
         assert p.exitcode == 0
     for rank, ok in got:
         assert ok == [True, True, True, True], (rank, ok)
+
+
+def _group_stream_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import pymra_b200.MRATools as mt
+    from pymra_b200.shard import GroupStreamBuild
+    from pymra_b200.structure import build_structure
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = []
+    for n, r, M, crit in [(300, 16, 4, 5), (300, 8, 3, 1)]:
+        locs = mt.genLocations2d(n)
+        np.random.seed(21)
+        want = build_structure(locs, r, M, 4, crit)
+        want_state = np.random.get_state()
+        np.random.seed(21 if rank == 0 else 99)
+        sb = GroupStreamBuild(locs, r, M, 4, crit)
+        good = sb.started and sb.wait(0)
+        st = sb.structure
+        good = good and np.array_equal(st.perm, want.perm) and np.array_equal(st.knot_rows[:r], want.knot_rows[:r])
+        for c in range(4):
+            good = good and sb.wait(1 + c)
+            for L in range(1, M):
+                lo = (int(st.level_off[L]) + c * 4 ** (L - 1)) * r
+                hi = lo + 4 ** (L - 1) * r
+                good = good and np.array_equal(st.knot_rows[lo:hi], want.knot_rows[lo:hi])
+        good = good and sb.finish() and sb.finish()
+        got_state = np.random.get_state()
+        good = good and all(np.array_equal(getattr(want, f), getattr(st, f)) for f in
+                            ("perm", "node_level", "node_parent", "node_kind", "node_row_start", "node_row_count",
+                             "node_child_start", "node_child_count", "node_knot_off", "knot_rows", "level_off"))
+        good = good and all(np.array_equal(want.node_kinds_local[k], st.node_kinds_local[k]) for k in (0, 2, want.n_nodes - 1))
+        good = good and np.array_equal(want_state[1], got_state[1]) and want_state[2] == got_state[2]
+        ok.append(bool(good))
+    # a ragged tree: every rank is told to fall back, nobody's RNG state moves
+    rng = np.random.RandomState(1)
+    locs = rng.uniform(size=(80000, 2))
+    np.random.seed(8)
+    before = np.random.get_state()
+    sb = GroupStreamBuild(locs, 10, 6, 4, 7)
+    res = [sb.wait(e) for e in range(5)] + [sb.finish()]
+    after = np.random.get_state()
+    ok.append(sb.started and not all(res) and res[-1] is False and np.array_equal(before[1], after[1]) and before[2] == after[2])
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_group_stream_build_forwards_events():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_group_stream_worker, args=(rk, 2, port, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok in got:
+        assert ok == [True, True, True], (rank, ok)
