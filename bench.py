@@ -253,6 +253,9 @@ def run_ours(args, rank, world, local_rank):
             e2e_breakdown = {k: round(v, 4) for k, v in tree.timings.items()}
             e2e_breakdown.update(wall_constructor=round(ta - t0, 4), wall_likelihood_predict_calls=round(tb - ta, 4),
                                  wall_total=round(time.time() - t0, 4))
+        if os.environ.get("MRA_BENCH_TRACE"):
+            print("[e2e step %d rank %d] %.4f s %s" % (i, rank, time.time() - t0,
+                                                      {k: round(v, 4) for k, v in tree.timings.items()}), file=sys.stderr, flush=True)
         # results dropped with the tree: otherwise the previous step's page-locked result buffer is still
         # referenced when the next step asks for one, and the first timed step pays a fresh cudaHostAlloc
         del tree, mean_h, sd_h

@@ -199,17 +199,15 @@ class GroupStreamBuild(object):
         if self.rank == 0:
             import os
             ncpu = os.cpu_count() or 8
-            saved = os.environ.get("MRA_BUILD_THREADS")
-            os.environ["MRA_BUILD_THREADS"] = str(ncpu if ncpu <= 8 else min(12, ncpu - 1))   # the other ranks wait
-            try:
-                if self.locs.ndim == 2 and self.locs.shape[1] == 2:
-                    self.sb = StreamBuild(self.locs, r, M, J, critDepth)
-            finally:
-                if saved is None:
-                    os.environ.pop("MRA_BUILD_THREADS", None)
-                else:
-                    os.environ["MRA_BUILD_THREADS"] = saved
+            # the other ranks wait: all host threads for this build (the job reads the variable when it starts its
+            # partition, so it is restored only after event 0)
+            self._saved_threads = ("MRA_BUILD_THREADS", os.environ.get("MRA_BUILD_THREADS"))
+            os.environ["MRA_BUILD_THREADS"] = str(ncpu if ncpu <= 8 else min(12, ncpu - 1))
+            if self.locs.ndim == 2 and self.locs.shape[1] == 2:
+                self.sb = StreamBuild(self.locs, r, M, J, critDepth)
             ok = 1 if (self.sb is not None and self.sb.started) else 0
+            if not ok:
+                self._restore_threads()
         head = self._bcast(np.array([ok], dtype=np.int32), 1)
         self.started = bool(head[0])
         self.N = len(self.locs)
@@ -217,18 +215,28 @@ class GroupStreamBuild(object):
         self.nk = (self.nn - 4 ** M) * r
         self.level_off = np.cumsum([0] + [4 ** m for m in range(M + 1)]).astype(np.int64)
 
+    def _restore_threads(self):
+        import os
+        saved = getattr(self, "_saved_threads", None)
+        if saved is not None:
+            self._saved_threads = None
+            if saved[1] is None:
+                os.environ.pop(saved[0], None)
+            else:
+                os.environ[saved[0]] = saved[1]
+
     # one int32 payload from rank 0 to everybody; non-root ranks sleep (not spin) while rank 0 is busy
     def _bcast(self, arr, n):
         torch, dist = self.torch, self.dist
-        if self.rank == 0:
-            t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32))
-        else:
-            t = torch.empty(n, dtype=torch.int32)
         if not self.on_gpu:
+            t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32)) if self.rank == 0 else torch.empty(n, dtype=torch.int32)
             dist.broadcast(t, src=self.src, group=self.group)
             return t.numpy()
         with torch.cuda.stream(self.comm):
-            t = t.to(self.dev, non_blocking=True)
+            if self.rank == 0:
+                t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32)).to(self.dev, non_blocking=True)
+            else:
+                t = torch.empty(n, dtype=torch.int32, device=self.dev)
             dist.broadcast(t, src=self.src, group=self.group)
             if self.rank == 0:
                 return arr
@@ -254,6 +262,7 @@ class GroupStreamBuild(object):
             msg = None
             if rank0:
                 ok = self.sb.wait(0)
+                self._restore_threads()
                 st = self.sb.structure
                 if ok:
                     msg = np.concatenate([np.array([1], dtype=np.int32), st.perm.astype(np.int32)]
