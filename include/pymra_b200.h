@@ -170,7 +170,7 @@ int mra_run_likelihood_top_async(mra_handle *h, void *stream, const double *dev_
 
 /* Streamed likelihood evaluation on one GPU, for overlapping the device passes with a host build that is still
  * drawing knots (mra_build_stream_*).  The subtrees of the root's children are the "parts" (mra_stream_parts;
- * 0 = not available: a leaf root, or a handle sharded below level 1).  mra_stream_begin_async resets the pass and runs the
+ * 0 = not available: a leaf root, or a handle sharded below level 2).  mra_stream_begin_async resets the pass and runs the
  * root's prior level (MRANode.py:378-395 for the root), which needs the root's knots only;
  * mra_stream_part_async(part) runs everything below the root for that subtree -- prior levels >= 1, leaf
  * terms (and, when predictions are planned, the leaf part of the predict pass), upward pass down to level 1
@@ -182,10 +182,12 @@ int mra_stream_parts(const mra_handle *h, int32_t *n_parts);
 int mra_stream_begin_async(mra_handle *h, void *stream, const int64_t *knot_rows);
 int mra_stream_part_async(mra_handle *h, void *stream, int32_t part, const int64_t *knot_rows);
 int mra_stream_end_async(mra_handle *h, void *stream);
-/* Handles sharded at level 1 (2-4 GPUs: the parts ARE the ranks' subtrees) stream the same way: every rank
- * calls mra_stream_begin_async (root prior level on its own rows), mra_stream_part_async for the parts it owns
- * (another rank's part is refused) and mra_stream_end_local_async, which exports the summaries like
+/* Sharded handles (shard level 1: 2-4 GPUs, the parts ARE the shards; level 2: up to 16 GPUs, a part is shared
+ * by the ranks that own subtrees inside it) stream the same way: every rank calls mra_stream_begin_async (root
+ * prior level on its own rows), mra_stream_part_async for the parts in its mra_stream_my_parts mask (others
+ * are refused) and mra_stream_end_local_async, which exports the summaries like
  * mra_run_likelihood_local_async; the caller all-reduces them and calls mra_run_likelihood_top_async. */
+int mra_stream_my_parts(const mra_handle *h, int32_t *mask);
 int mra_stream_end_local_async(mra_handle *h, void *stream, double *dev_summary);
 
 /* Counters for bench.py: kernels launched by the last run_* call, and algorithmic FP64

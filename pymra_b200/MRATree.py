@@ -166,7 +166,7 @@ class MRATree(object):
             from .shard import GroupStreamBuild
             g = None if group is True else group
             world, rank = dist.get_world_size(g), dist.get_rank(g)
-            if world > 4 or len(locs_c) < 65536 or M < 1 or M > 12:     # deterministic on every rank
+            if world > 16 or len(locs_c) < 65536 or M < 1 or M > 12:    # deterministic on every rank
                 return
             sb = GroupStreamBuild(locs_c, r, M, J, critDepth, g)
         if not sb.started:
@@ -187,7 +187,8 @@ class MRATree(object):
                 nparts = session.n_parts()
             del staged
             t3 = time.perf_counter()
-            streamable = ok and nparts == 4 and session.shard_level == (0 if world == 1 else 1)
+            streamable = ok and nparts == 4 and session.shard_level <= 2 and (world == 1) == (session.shard_level == 0)
+            mine = session.my_parts() if streamable else []
             if streamable:
                 session.stream_begin()
             waits = 0.0
@@ -195,7 +196,7 @@ class MRATree(object):
                 tw = time.perf_counter()
                 ok = sb.wait(1 + c) and ok
                 waits += time.perf_counter() - tw
-                if ok and streamable and c % world == rank:
+                if ok and streamable and c in mine:
                     session.stream_part(c)
             tw = time.perf_counter()
             ok = sb.finish() and ok

@@ -61,6 +61,7 @@ SIGNATURES = {
     "mra_stream_begin_async": (C.c_int, [C.c_void_p, C.c_void_p, _p64]),
     "mra_stream_part_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _p64]),
     "mra_stream_end_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mra_stream_my_parts": (C.c_int, [C.c_void_p, _p32]),
     "mra_stream_end_local_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mra_last_launches": (C.c_int, [C.c_void_p, _p64]),
     "mra_last_flops": (C.c_int, [C.c_void_p, _pd, _pd]),

@@ -53,6 +53,8 @@ struct mra_handle {
   std::vector<int> leaves;                     // node ids of leaves + orphans
   std::vector<std::vector<int4>> ptiles_at;    // prior pass: 64-row tiles per level (+ gathered knot tiles when sharded)
   std::vector<int> gather_rows;                // row ids of the gathered tiles
+  std::vector<int2> gather_node;               // (top node, first slot in gather_rows): r slots each
+  std::vector<int> n_regular_tiles;            // per level: tiles of ptiles_at that are not gathered tiles
   std::vector<int4> leaf_tiles;                // 64-row tiles of leaves / orphans (fused predict pass)
   std::vector<int4> fold_items;                // (node, ancestor level, row tile, column tile) of k_fold
   std::vector<int2> emit_chunks;               // row ranges whose results this rank emits
@@ -67,6 +69,8 @@ struct mra_handle {
   std::vector<std::vector<Range>> part_nodes, part_tiles;   // [level][part] into internal_at / ptiles_at
   std::vector<std::vector<Range>> part_leaves;              // [part] -> ranges of `leaves`
   std::vector<std::vector<Range>> part_knots;               // [part] -> ranges of knot_rows
+  std::vector<Range> part_gtiles;                           // [part] -> gathered tiles of its level-1 node in ptiles_at[0]
+  std::vector<int2> part_gather;                            // [part] -> (level-1 top node, first slot in gather_rows) or (-1, 0)
   int stream_parts_done = 0;                                // bit mask of the parts run since mra_stream_begin_async
   int my_parts = 0;                                         // bit mask of the parts this rank evaluates (all when unsharded)
   bool stream_open = false, leafq_done = false;
@@ -508,8 +512,10 @@ void build_lists(mra_handle* h) {
       }
     }
     add_emit(0, h->N);
+    h->n_regular_tiles.assign(nlev, 0);
+    for (size_t m = 0; m < nlev; ++m) h->n_regular_tiles[m] = (int)h->ptiles_at[m].size();
+    h->gather_node.clear();
   } else {
-    std::vector<char> covered((size_t)h->N, 0);
     for (int n = 0; n < nn; ++n) {
       const int role = h->role[n], lv = h->level[n];
       if (!role) continue;
@@ -519,27 +525,27 @@ void build_lists(mra_handle* h) {
       if (lv == s) h->sroots.push_back(n);
       const bool piece = (lv == s) || (lv < s && !internal);
       if (piece) {
-        std::fill(covered.begin() + h->row_start[n], covered.begin() + h->row_start[n] + h->row_count[n], 1);
         for (int a = h->parent[n]; a >= 0; a = h->parent[a]) add_tiles(a, h->row_start[n], h->row_count[n]);
         if (role == 1 || role == 3) add_emit(h->row_start[n], h->row_count[n]);
       }
       if (lv >= s && internal) add_tiles(n, h->row_start[n], h->row_count[n]);
     }
+    // The knots of a replicated top node at levels 1 .. s-1 may lie anywhere below it, also in other ranks'
+    // subtrees, and knot_factor needs the ancestors' basis at those rows: all r knot rows of every such node are
+    // "gathered" into extra tiles of the ancestors' levels.  The lists have a fixed shape (r rows per node), so
+    // they can be laid out before the knots are drawn; refresh_gather_rows() fills in the row ids.
+    h->n_regular_tiles.assign(nlev, 0);
+    for (size_t m = 0; m < nlev; ++m) h->n_regular_tiles[m] = (int)h->ptiles_at[m].size();
+    h->gather_node.clear();
     for (int n = 0; n < nn; ++n) {
       const int lv = h->level[n];
       if (h->role[n] < 2 || h->kind[n] != KIND_INTERNAL || lv < 1 || lv >= s) continue;
-      const size_t g0 = h->gather_rows.size();
-      for (int i = 0; i < h->r; ++i) {
-        const int row = h->knot_rows[h->knot_off[n] + i];
-        if (!covered[row]) {
-          covered[row] = 1;   // a knot is used by exactly one node; keeps duplicates out all the same
-          h->gather_rows.push_back(row);
-        }
-      }
-      const int cnt = (int)(h->gather_rows.size() - g0);
+      const int g0 = (int)h->gather_rows.size();
+      h->gather_node.push_back(make_int2(n, g0));
+      for (int i = 0; i < h->r; ++i) h->gather_rows.push_back(h->knot_rows[h->knot_off[n] + i]);
       for (int a = h->parent[n]; a >= 0; a = h->parent[a])
-        for (int r0 = 0; r0 < cnt; r0 += TB)
-          h->ptiles_at[h->level[a]].push_back(make_int4(a, 0, std::min(TB, cnt - r0), (int)(g0 + r0) + 1));
+        for (int r0 = 0; r0 < h->r; r0 += TB)
+          h->ptiles_at[h->level[a]].push_back(make_int4(a, 0, std::min(TB, h->r - r0), g0 + r0 + 1));
     }
   }
   while (!h->internal_at.empty() && h->internal_at.back().empty()) {
@@ -550,13 +556,19 @@ void build_lists(mra_handle* h) {
   for (int n : h->leaves)
     for (int64_t r0 = 0; r0 < h->row_count[n]; r0 += TB)
       h->leaf_tiles.push_back(make_int4(n, (int)(h->row_start[n] + r0), (int)std::min<int64_t>(TB, h->row_count[n] - r0), 0));
-  // parts for the streamed evaluation: the subtree of every child of the root is a contiguous range of each list
+  // parts for the streamed evaluation: the subtree of every child of the root is a contiguous range of each list.
+  // Unsharded: every part is mine.  Sharded at level 1: the parts are the shards.  Sharded at level 2: a part is
+  // mine when one of my subtrees lies in it; its level-1 node is a replicated top node whose gathered knot tiles
+  // (level 0) belong to the part as well.
   h->n_parts = 0;
+  h->my_parts = 0;
   h->part_nodes.clear();
   h->part_tiles.clear();
+  h->part_gtiles.clear();
   h->part_leaves.clear();
   h->part_knots.clear();
-  if (s <= 1 && nn > 1 && h->kind[0] == KIND_INTERNAL && !h->internal_at.empty()) {
+  h->part_gather.clear();
+  if (s <= 2 && nn > 1 && h->kind[0] == KIND_INTERNAL && !h->internal_at.empty()) {
     const int np = h->child_count[0], c0 = h->child_start[0];
     std::vector<int> part_of((size_t)nn, -1);
     for (int n = 1; n < nn; ++n) part_of[n] = h->parent[n] == 0 ? n - c0 : part_of[h->parent[n]];
@@ -564,45 +576,65 @@ void build_lists(mra_handle* h) {
     const size_t nl = h->internal_at.size();
     h->part_nodes.assign(nl, std::vector<Range>(np, Range{0, 0}));
     h->part_tiles.assign(nl, std::vector<Range>(np, Range{0, 0}));
+    h->part_gtiles.assign(np, Range{0, 0});
     h->part_leaves.assign(np, {});
     h->part_knots.assign(np, {});
+    h->part_gather.assign(np, make_int2(-1, 0));
     auto extend = [](Range& rg, int i) {
       if (rg.count == 0) rg.begin = i;
       ++rg.count;
     };
-    bool ok = true;
-    for (size_t m = 1; m < nl; ++m) {
+    bool ok = np <= 30;
+    for (size_t m = 1; m < nl && ok; ++m) {
       int last = -1;
       for (int i = 0; i < (int)h->internal_at[m].size(); ++i) {
         const int n = h->internal_at[m][i], pp = part_of[n];
         if (pp < last) ok = false;
         last = pp;
         extend(h->part_nodes[m][pp], i);
+        if (h->role[n] == 1) h->my_parts |= 1 << pp;
         std::vector<Range>& kr = h->part_knots[pp];
         const int ko = (int)h->knot_off[n];
         if (!kr.empty() && kr.back().begin + kr.back().count == ko) kr.back().count += h->r;
         else kr.push_back(Range{ko, h->r});
       }
       last = -1;
-      for (int i = 0; i < (int)h->ptiles_at[m].size(); ++i) {
+      for (int i = 0; i < h->n_regular_tiles[m]; ++i) {
         const int pp = part_of[h->ptiles_at[m][i].x];
         if (pp < last) ok = false;
         last = pp;
         extend(h->part_tiles[m][pp], i);
       }
+      if (h->n_regular_tiles[m] != (int)h->ptiles_at[m].size()) ok = false;   // gathered tiles below level 0: s > 2
     }
-    for (int i = 0; i < (int)h->leaves.size(); ++i) {
-      std::vector<Range>& lr = h->part_leaves[part_of[h->leaves[i]]];
+    for (int i = 0; i < (int)h->leaves.size() && ok; ++i) {
+      const int n = h->leaves[i];
+      if (h->role[n] != 1 && s > 0) {       // a replicated leaf above the shard level: not streamed
+        ok = false;
+        break;
+      }
+      h->my_parts |= 1 << part_of[n];
+      std::vector<Range>& lr = h->part_leaves[part_of[n]];
       if (!lr.empty() && lr.back().begin + lr.back().count == i) ++lr.back().count;
       else lr.push_back(Range{i, 1});
     }
-    if (np > 30) ok = false;
-    h->my_parts = 0;
-    for (int pp = 0; pp < np && ok; ++pp) {
-      const int child = c0 + pp;
-      if (s == 0 || h->role[child] == 1) h->my_parts |= 1 << pp;
-      else if (h->role[child] != 0) ok = false;          // a replicated leaf child of the root: not streamed
+    // gathered tiles of the level-1 top nodes (sharded at level 2) sit behind the regular tiles of level 0
+    for (const int2& gn : h->gather_node) {
+      if (h->level[gn.x] != 1) {
+        ok = false;
+        break;
+      }
+      h->part_gather[part_of[gn.x]] = gn;
     }
+    for (int i = h->n_regular_tiles[0]; i < (int)h->ptiles_at[0].size() && ok; ++i) {
+      const int slot = h->ptiles_at[0][i].w - 1;
+      int pp = -1;
+      for (const int2& gn : h->gather_node)
+        if (slot >= gn.y && slot < gn.y + h->r) pp = part_of[gn.x];
+      if (pp < 0) ok = false;
+      else extend(h->part_gtiles[pp], i);
+    }
+    if (s == 0) h->my_parts = (1 << np) - 1;
     if (!ok) h->n_parts = 0;      // streaming is refused then
   }
 }
@@ -1135,12 +1167,19 @@ int mra_run_likelihood_top_async(mra_handle* h, void* stream, const double* dev_
 
 int mra_stream_parts(const mra_handle* h, int32_t* n_parts) {
   if (!h || !n_parts) return MRA_ERR_ARG;
-  *n_parts = h->shard_level <= 1 ? h->n_parts : 0;
+  *n_parts = h->shard_level <= 2 ? h->n_parts : 0;
+  return MRA_OK;
+}
+
+int mra_stream_my_parts(const mra_handle* h, int32_t* mask) {
+  if (!h || !mask) return MRA_ERR_ARG;
+  *mask = h->shard_level <= 2 && h->n_parts > 0 ? h->my_parts : 0;
   return MRA_OK;
 }
 
 // uploads ranges of the caller's knot_rows (tree-order row ids) on the copy stream and makes `st` wait for them
-static int upload_knot_ranges(mra_handle* h, cudaStream_t st, const int64_t* knot_rows, const std::vector<Range>& ranges) {
+static int upload_knot_ranges(mra_handle* h, cudaStream_t st, const int64_t* knot_rows, const std::vector<Range>& ranges,
+                              int2 gather = make_int2(-1, 0)) {
   if (!knot_rows || ranges.empty()) return MRA_OK;
   if (!h->copy_stream) {
     CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -1154,6 +1193,11 @@ static int upload_knot_ranges(mra_handle* h, cudaStream_t st, const int64_t* kno
     CU(cudaMemcpyAsync(h->ws + h->lay.knot_rows + sizeof(int) * (size_t)rg.begin, h->knot_rows.data() + rg.begin,
                        sizeof(int) * (size_t)rg.count, cudaMemcpyHostToDevice, h->copy_stream));
   }
+  if (gather.x >= 0) {      // the gathered knot rows of a replicated top node follow its knots
+    for (int i = 0; i < h->r; ++i) h->gather_rows[gather.y + i] = h->knot_rows[h->knot_off[gather.x] + i];
+    CU(cudaMemcpyAsync(h->ws + h->lay.gather + sizeof(int) * (size_t)gather.y, h->gather_rows.data() + gather.y,
+                       sizeof(int) * (size_t)h->r, cudaMemcpyHostToDevice, h->copy_stream));
+  }
   CU(cudaEventRecord(h->copy_event, h->copy_stream));
   CU(cudaStreamWaitEvent(st, h->copy_event, 0));
   return MRA_OK;
@@ -1161,8 +1205,8 @@ static int upload_knot_ranges(mra_handle* h, cudaStream_t st, const int64_t* kno
 
 int mra_stream_begin_async(mra_handle* h, void* stream, const int64_t* knot_rows) {
   if (!h) return MRA_ERR_ARG;
-  if (h->shard_level > 1 || h->n_parts <= 0)
-    return fail(h, MRA_ERR_STATE, "streamed evaluation needs an internal root and a handle that is unsharded or sharded at level 1");
+  if (h->shard_level > 2 || h->n_parts <= 0)
+    return fail(h, MRA_ERR_STATE, "streamed evaluation needs an internal root and a handle that is unsharded or sharded at level 1 or 2");
   int rc = ready_to_run(h);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1172,7 +1216,7 @@ int mra_stream_begin_async(mra_handle* h, void* stream, const int64_t* knot_rows
   if (rc) return rc;
   rc = upload_knot_ranges(h, st, knot_rows, std::vector<Range>{Range{(int)h->knot_off[0], h->r}});
   if (rc) return rc;
-  rc = prior_level(h, st, c, 0, Range{0, (int)h->internal_at[0].size()}, Range{0, (int)h->ptiles_at[0].size()});
+  rc = prior_level(h, st, c, 0, Range{0, (int)h->internal_at[0].size()}, Range{0, h->n_regular_tiles[0]});
   if (rc) return rc;
   CU(cudaGetLastError());
   h->stream_open = true;
@@ -1189,9 +1233,13 @@ int mra_stream_part_async(mra_handle* h, void* stream, int32_t part, const int64
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CU(cudaSetDevice(h->device));
   DevCtx c = make_ctx(h);
-  int rc = upload_knot_ranges(h, st, knot_rows, h->part_knots[part]);
+  int rc = upload_knot_ranges(h, st, knot_rows, h->part_knots[part], h->part_gather[part]);
   if (rc) return rc;
   const int nl = (int)h->internal_at.size();
+  if (h->part_gtiles[part].count > 0) {     // sharded at level 2: the root's basis at the knots of the part's level-1 node
+    const int4* tl = reinterpret_cast<const int4*>(h->ws + h->lay.ptiles + h->ptiles_off[0]) + h->part_gtiles[part].begin;
+    MRA_FOR_VEC(h, LAUNCH("prior_tiles", k_prior_tiles<V_><<<h->part_gtiles[part].count, NT, smem_prior(h->r), st>>>(c, tl, 0)));
+  }
   for (int m = 1; m < nl; ++m) {
     rc = prior_level(h, st, c, m, h->part_nodes[m][part], h->part_tiles[m][part]);
     if (rc) return rc;
@@ -1204,7 +1252,7 @@ int mra_stream_part_async(mra_handle* h, void* stream, int32_t part, const int64
       if (rc) return rc;
     }
   }
-  for (int m = nl - 1; m >= 1; --m) {
+  for (int m = nl - 1; m >= std::max(1, h->shard_level); --m) {
     rc = upward_level(h, st, c, m, h->part_nodes[m][part]);
     if (rc) return rc;
   }
@@ -1230,7 +1278,8 @@ int mra_stream_end_async(mra_handle* h, void* stream) {
 
 int mra_stream_end_local_async(mra_handle* h, void* stream, double* dev_summary) {
   if (!h) return MRA_ERR_ARG;
-  if (h->shard_level != 1) return fail(h, MRA_ERR_STATE, "mra_stream_end_local_async is for handles sharded at level 1");
+  if (h->shard_level < 1 || h->shard_level > 2)
+    return fail(h, MRA_ERR_STATE, "mra_stream_end_local_async is for handles sharded at level 1 or 2");
   if (!dev_summary) return fail(h, MRA_ERR_ARG, "sharded handle needs a summary buffer");
   if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
   if (h->stream_parts_done != h->my_parts) return fail(h, MRA_ERR_STATE, "not every part of this rank has been evaluated");

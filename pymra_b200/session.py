@@ -146,6 +146,12 @@ class DeviceSession(object):
         self.check(self.lib.mra_stream_parts(self.h, C.byref(n)))
         return int(n.value)
 
+    def my_parts(self):
+        """Parts this rank evaluates in a streamed pass (all of them when unsharded)."""
+        m = C.c_int32()
+        self.check(self.lib.mra_stream_my_parts(self.h, C.byref(m)))
+        return [p for p in range(31) if (int(m.value) >> p) & 1]
+
     def _knots_ptr(self):
         # the int64 array mra_set_structure was given; for a streamed build it is the array the builder fills
         return self._knot_rows_i64.ctypes.data_as(C.POINTER(C.c_int64))

@@ -84,10 +84,10 @@ def test_stream_parts_in_any_order_and_call_order_errors():
     s.close()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_emulated_level1_shards_stream_their_parts(world):
-    """Handles sharded at level 1 (2-4 GPUs) stream the parts they own: same summaries, likelihood and
-    predictions as the plain sharded pass; another rank's part is refused."""
+@pytest.mark.parametrize("world", [2, 4, 8, 16])
+def test_emulated_shards_stream_their_parts(world):
+    """Handles sharded at level 1 (2-4 GPUs) or 2 (8-16 GPUs) stream the parts they own: same summaries,
+    likelihood and predictions as the plain sharded pass; another rank's part is refused."""
     import torch
     import pymra_b200.MRATools as mt
     from pymra_b200 import _ffi
@@ -103,7 +103,7 @@ def test_emulated_level1_shards_stream_their_parts(world):
     for rank in range(world):
         s = DeviceSession(st, locs, y, want_predict=True, emulate=(world, rank))
         s.set_params(cov, 1e-2)
-        assert s.shard_level == 1 and s.n_parts() == 4
+        assert s.shard_level == (1 if world <= 4 else 2) and s.n_parts() == 4
         sess.append(s)
 
     def finish(total):
@@ -124,11 +124,14 @@ def test_emulated_level1_shards_stream_their_parts(world):
     want = finish(want_total.clone())
     for rank, s in enumerate(sess):
         s.stream_begin()
-        with pytest.raises(_ffi.MraError):
-            s.stream_part((rank + 1) % world)              # owned by the next rank (round-robin)
-        for part in reversed(range(4)):
-            if part % world == rank:
-                s.stream_part(part)
+        mine = s.my_parts()
+        assert mine == ([p for p in range(4) if p % world == rank] if world <= 4 else
+                        sorted({(k // 4) for k in range(16) if k % world == rank}))
+        for other in set(range(4)) - set(mine):
+            with pytest.raises(_ffi.MraError):
+                s.stream_part(other)                       # no subtree of mine in there
+        for part in reversed(mine):
+            s.stream_part(part)
         s.stream_end_local()
     got_total = torch.stack([s.summary for s in sess]).sum(0)
     assert torch.equal(got_total, want_total)
