@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <utility>
 #include <string>
 #include <thread>
 #include <vector>
@@ -19,6 +21,18 @@
 using namespace mra;
 
 namespace {
+
+// vector storage that is filled right after resize(): skips the zero-fill of the O(N) host tables
+template <class T>
+struct NoInit : std::allocator<T> {
+  template <class U>
+  struct rebind { using other = NoInit<U>; };
+  template <class U>
+  void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... Args>
+  void construct(U* p, Args&&... args) { ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...); }
+};
+using IntBuf = std::vector<int, NoInit<int>>;
 
 struct Arena {
   size_t off = 0;
@@ -47,7 +61,8 @@ struct mra_handle {
   int dim = 0, r = 0, depth = 0, n_nodes = 0;
   std::vector<int> level, parent, kind, child_start, child_count, level_off;
   std::vector<int64_t> row_start, row_count, knot_off;
-  std::vector<int> knot_rows, perm;
+  std::vector<int> knot_rows;
+  IntBuf perm;
   // derived lists
   std::vector<std::vector<int>> internal_at;   // node ids per level
   std::vector<int> leaves;                     // node ids of leaves + orphans
@@ -79,7 +94,7 @@ struct mra_handle {
   int slot_base = 0, n_slots = 0;
   size_t sroots_off = 0;
   std::vector<NodeDev> nodes;
-  std::vector<int> obs_rows, unobs_rows;
+  IntBuf obs_rows, unobs_rows;
   int max_leaf_obs = 0, max_leaf_rows = 0, max_leaf_W = 1, max_leaf_unobs = 0;
   int64_t n_obs_total = 0;
   long long ldv = 0;
@@ -491,6 +506,12 @@ void build_lists(mra_handle* h) {
   h->gather_rows.clear();
   h->emit_chunks.clear();
   h->sroots.clear();
+  {
+    std::vector<int64_t> rows_at(nlev, 0);
+    for (int n = 0; n < nn; ++n)
+      if (h->kind[n] == KIND_INTERNAL) rows_at[h->level[n]] += h->row_count[n] / TB + 1;
+    for (size_t m = 0; m < nlev; ++m) h->ptiles_at[m].reserve((size_t)rows_at[m] + 8);
+  }
   auto add_tiles = [&](int node, int64_t row0, int64_t cnt) {
     const int lv = h->level[node];
     for (int64_t r0 = 0; r0 < cnt; r0 += TB) {
@@ -757,7 +778,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   h->max_leaf_W = 1;
   for (auto& f : h->kflops) f = 0.0;
   for (auto& f : h->kbytes) f = 0.0;
-  std::vector<uint8_t> finite_row((size_t)h->N);     // np.isfinite(obs) in tree order (MRANode.py:415)
+  std::vector<uint8_t, NoInit<uint8_t>> finite_row((size_t)h->N);     // np.isfinite(obs) in tree order (MRANode.py:415)
   {
     uint8_t* fr = finite_row.data();
     const int* pm = h->perm.data();
@@ -909,6 +930,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   h->fold_items.clear();
   if (h->want_predict) {
     const int nct = (r + TB - 1) / TB;
+    h->fold_items.reserve((size_t)nn * (size_t)std::max(1, h->depth) * nct * 2);
     for (int n = 0; n < nn; ++n) {
       const NodeDev& d = h->nodes[n];
       if (!h->role[n] || d.level < 1) continue;

@@ -119,3 +119,72 @@ def test_nccl_two_ranks_match_reference(name):
         rl, em, es = errs(lik, mean, sd, g)
         assert rl <= max(1e-9, 20 * fl) and em <= max(1e-9, 20 * fm) and es <= max(1e-9, 20 * fs)
     assert got[0][2] == got[1][2]
+
+
+def _nccl_stream_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import pymra_b200.MRATools as mt
+    from pymra_b200.MRATree import MRATree
+    locs, y = _stream_case()
+    np.random.seed(5 if rank == 0 else 77)                 # a native tree is rank 0's draw
+    t = MRATree(locs, 16, lambda a, b: mt.Matern32(a, b, l=0.3, sig=1.0), y, 1e-2, M=4, group=True)
+    state = np.random.get_state()
+    lik = float(np.asarray(t.getLikelihood()).ravel()[0])
+    mean, sd = t.predict()
+    q.put((rank, t.timings.get("streamed"), lik, np.asarray(mean).ravel(), sd, state[1][:8].copy(), int(state[2])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _stream_case():
+    import pymra_b200.MRATools as mt
+    locs = mt.genLocations2d(300)
+    N = len(locs)
+    rng = np.random.RandomState(3)
+    sel = np.sort(rng.choice(N, int(0.4 * N), replace=False))
+    y = np.full((N, 1), np.nan)
+    y[sel] = np.sin(5.0 * locs[sel, :1]) + 0.3 * rng.normal(size=(len(sel), 1))
+    return locs, y
+
+
+def test_nccl_two_ranks_streamed_group_build(monkeypatch):
+    """>= 65536 locations: rank 0 builds and forwards the events, both ranks stream their subtrees; the result
+    equals the plain single-GPU construction from rank 0's RNG state, and both ranks end with its RNG state."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import pymra_b200.MRATools as mt
+    from pymra_b200.MRATree import MRATree
+    locs, y = _stream_case()
+    monkeypatch.setenv("PYMRA_B200_STREAM", "0")
+    np.random.seed(5)
+    t = MRATree(locs, 16, lambda a, b: mt.Matern32(a, b, l=0.3, sig=1.0), y, 1e-2, M=4)
+    want_state = np.random.get_state()
+    lik1 = float(np.asarray(t.getLikelihood()).ravel()[0])
+    mean1, sd1 = t.predict()
+    mean1 = np.asarray(mean1).ravel().copy()
+    sd1 = sd1.copy()
+    del t
+    monkeypatch.setenv("PYMRA_B200_STREAM", "1")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_stream_worker, args=(rk, 2, port, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, streamed, lik, mean, sd, key8, pos in got:
+        assert streamed == 1.0
+        assert abs(lik - lik1) <= 1e-12 * abs(lik1)
+        assert np.max(np.abs(mean - mean1)) <= 1e-11 and np.max(np.abs(sd - sd1)) <= 1e-11
+        assert np.array_equal(key8, want_state[1][:8]) and pos == int(want_state[2])
+    assert got[0][2] == got[1][2]
