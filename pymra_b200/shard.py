@@ -171,6 +171,17 @@ def build_structure_group(locs, r, M, J, critDepth, group=None, async_start=None
     return st
 
 
+_COMM_STREAMS = {}
+
+
+def _comm_stream(dev):
+    import torch
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _COMM_STREAMS:
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=dev, priority=-1)
+    return _COMM_STREAMS[key]
+
+
 class GroupStreamBuild(object):
     """StreamBuild (pymra_b200/structure.py) for a process group: rank 0 runs the streaming native builder and
     forwards every progress event with the arrays that became final -- event 0: permutation, node table and the
@@ -189,7 +200,10 @@ class GroupStreamBuild(object):
         self.src = dist.get_global_rank(group, 0) if group is not None else 0
         self.on_gpu = dist.get_backend(group) == "nccl"
         self.dev = torch.device("cuda", torch.cuda.current_device()) if self.on_gpu else torch.device("cpu")
-        self.comm = torch.cuda.Stream(priority=-1) if self.on_gpu else None
+        # one side stream per device for the whole process: the caching allocator keeps a pool per stream, so a
+        # fresh stream per construction would mean fresh cudaMallocs (slow, and synchronising, once NCCL has
+        # enabled peer access) for every forwarded payload
+        self.comm = _comm_stream(self.dev) if self.on_gpu else None
         self.locs = np.ascontiguousarray(locs, dtype=np.float64)
         self.r, self.M, self.J = r, M, J
         self.sb = None
