@@ -210,10 +210,10 @@ def run_ours(args, rank, world, local_rank):
         sess.likelihood_async()
         sess.predict_dev(mean_t, sd_t, reduce=True)   # N > 1: outputs sum-reduced so every rank holds all N rows
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None     # polls over the warm-up and the timed steps
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     sess.profile_enable(True)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
