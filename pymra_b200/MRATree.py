@@ -150,9 +150,8 @@ class MRATree(object):
         """Large regular 2-D trees: the C++ builder runs on its own thread (StreamBuild) and the device passes
         start as soon as the RNG-independent part of the tree (partition, permutation, the root's knots) is
         known; each subtree of the root is evaluated when the sequential knot draw (MRANode.py:191-193, DFS
-        pre-order) has left it.  With a process group of 2-4 ranks (sharded at level 1, so the root's subtrees
-        ARE the shards) rank 0 builds and forwards every event (GroupStreamBuild) and each rank evaluates the
-        subtrees it owns.  Same results and RNG consumption as the plain path; leaves self._session = None
+        pre-order) has left it.  With a process group (up to 16 ranks: sharded at level 1 or 2) rank 0 builds and
+        forwards every event (GroupStreamBuild) and each rank evaluates the root subtrees that hold its shards.  Same results and RNG consumption as the plain path; leaves self._session = None
         (global RNG untouched) when the tree is outside this path."""
         import torch
         if not torch.cuda.is_available():
