@@ -148,7 +148,9 @@ def run_reference(args, rank, world):
     cores = os.cpu_count()
     sample = ("oracle/mra_oracle.py (NumPy/LAPACK restatement of pyMRA, gc.collect not called) on a %dx%d grid, "
               "r0=%d: one level-3 subtree of the workload, same leaf sizes; %.0f locs/s scaled by 1/N to evals/s "
-              "(optimistic for the CPU: the full tree is 3 levels deeper)" % (SAMPLE_GRID, SAMPLE_GRID, r, locs_s))
+              "(optimistic for the CPU twice over: the full tree is 3 levels deeper, and on these very inputs the "
+              "unmodified reference takes 9.4x (gc.collect stubbed) to 13x (as is) longer than this port -- "
+              "profiles/r03_reference_vs_port_build_container.jsonl)" % (SAMPLE_GRID, SAMPLE_GRID, r, locs_s))
     line = {"impl": "reference", "metric": "getLikelihood() evals/sec and predict() locations/sec at n=4M",
             "value": evals, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -304,7 +306,9 @@ def run_ours(args, rank, world, local_rank):
         evals, locs_s, per = cpu_baseline(r, Mreq, family, l, sig, R, frac, N)
         cb = {"value": evals, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
               "sample": "oracle/mra_oracle.py on a %dx%d grid, r0=%d (one level-3 subtree of the workload, same leaf "
-                        "sizes): %.1f s, %.0f locs/s, scaled by 1/N" % (SAMPLE_GRID, SAMPLE_GRID, r, per, locs_s)}
+                        "sizes): %.1f s, %.0f locs/s, scaled by 1/N; the unmodified reference is 9.4-13x slower than "
+                        "this port on the same inputs (profiles/r03_reference_vs_port_build_container.jsonl)"
+                        % (SAMPLE_GRID, SAMPLE_GRID, r, per, locs_s)}
 
     line = {"metric": "getLikelihood() evals/sec and predict() locations/sec at n=4M",
             "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
