@@ -530,22 +530,55 @@ struct Partitioner {
     cnt[3] = nxy;
   }
 
-  void do_node(const PNode& nd, PNode* ch, int b) {
+  // A node is partitioned in two passes: classify() writes the quadrant codes of its rows and counts them (all
+  // the bit planes need, so a level can be published to the RNG replay before any row has moved), scatter() then
+  // moves rows / coordinates into the children's ranges and forms the children's column sums.
+  struct NodePlan {
+    int64_t cnt[4] = {0, 0, 0, 0}, off[4] = {0, 0, 0, 0};
+    std::vector<int64_t> cc;      // cooperative path: per-chunk counts
+    int nc = 0;
+    int64_t step = 0;
+  };
+
+  void classify(const PNode& nd, int b, NodePlan& pl) {
     const int64_t n = nd.e - nd.s;
     if (n <= 100) {
       failed.store(1);
       return;
     }
     const double mx = nd.sx / (double)n, my = nd.sy / (double)n;
+    const double *X = xs[b], *Y = ys[b];
+    if (n < BIG) {
+      pass1(X, Y, code, nd.s, nd.e, mx, my, pl.cnt);
+    } else {
+      // cooperative path: all threads on one node, chunked codes
+      pl.nc = nthreads * 4;
+      pl.step = (n + pl.nc - 1) / pl.nc;
+      pl.cc.assign((size_t)pl.nc * 4, 0);
+      run_parallel(nthreads, pl.nc, [&](int64_t k) {
+        const int64_t a = nd.s + k * pl.step, bb = std::min(nd.e, a + pl.step);
+        if (a < bb) pass1(X, Y, code, a, bb, mx, my, &pl.cc[4 * k]);
+      });
+      for (int c = 0; c < 4; ++c) {
+        pl.cnt[c] = 0;
+        for (int k = 0; k < pl.nc; ++k) pl.cnt[c] += pl.cc[4 * k + c];
+      }
+    }
+    pl.off[0] = nd.s;
+    for (int c = 1; c < 4; ++c) pl.off[c] = pl.off[c - 1] + pl.cnt[c - 1];
+    for (int c = 0; c < 4; ++c)
+      if (pl.cnt[c] == 0) failed.store(1);
+  }
+
+  void scatter(const PNode& nd, PNode* ch, int b, const NodePlan& pl) {
+    const int64_t n = nd.e - nd.s;
     const int32_t* R = rows[b];
     const double *X = xs[b], *Y = ys[b];
     int32_t* R2 = rows[b ^ 1];
     double *X2 = xs[b ^ 1], *Y2 = ys[b ^ 1];
-    int64_t cnt[4], off[4];
+    const int64_t* cnt = pl.cnt;
+    const int64_t* off = pl.off;
     if (n < BIG) {
-      pass1(X, Y, code, nd.s, nd.e, mx, my, cnt);
-      off[0] = nd.s;
-      for (int c = 1; c < 4; ++c) off[c] = off[c - 1] + cnt[c - 1];
       int64_t w[4] = {off[0], off[1], off[2], off[3]};
       double csx[4] = {0, 0, 0, 0}, csy[4] = {0, 0, 0, 0};
       for (int64_t i = nd.s; i < nd.e; ++i) {
@@ -560,27 +593,16 @@ struct Partitioner {
       }
       for (int c = 0; c < 4; ++c) ch[c] = PNode{off[c], off[c] + cnt[c], csx[c], csy[c]};
     } else {
-      // cooperative path: all threads on one node (chunked codes, chunked stable scatter, then the
-      // children's sums one thread each, in row order as np.mean needs)
-      const int nc = nthreads * 4;
-      const int64_t step = (n + nc - 1) / nc;
-      std::vector<int64_t> cc((size_t)nc * 4, 0);
-      run_parallel(nthreads, nc, [&](int64_t k) {
-        const int64_t a = nd.s + k * step, bb = std::min(nd.e, a + step);
-        if (a < bb) pass1(X, Y, code, a, bb, mx, my, &cc[4 * k]);
-      });
-      for (int c = 0; c < 4; ++c) {
-        cnt[c] = 0;
-        for (int k = 0; k < nc; ++k) cnt[c] += cc[4 * k + c];
-      }
-      off[0] = nd.s;
-      for (int c = 1; c < 4; ++c) off[c] = off[c - 1] + cnt[c - 1];
+      // cooperative path: chunked stable scatter, then the children's sums one thread each, in row order as
+      // np.mean needs
+      const int nc = pl.nc;
+      const int64_t step = pl.step;
       std::vector<int64_t> w0((size_t)nc * 4);
       for (int c = 0; c < 4; ++c) {
         int64_t acc = off[c];
         for (int k = 0; k < nc; ++k) {
           w0[4 * k + c] = acc;
-          acc += cc[4 * k + c];
+          acc += pl.cc[4 * k + c];
         }
       }
       run_parallel(nthreads, nc, [&](int64_t k) {
@@ -602,8 +624,6 @@ struct Partitioner {
         ch[c] = PNode{off[c], off[c] + cnt[c], sx, sy};
       });
     }
-    for (int c = 0; c < 4; ++c)
-      if (cnt[c] == 0) failed.store(1);
   }
 
   // bit planes + cumulative block counts of positions [s0, e0) from the code bytes; nt threads
@@ -664,12 +684,15 @@ struct Partitioner {
   // levels S .. M-1 of the subtree rooted at `root` (a level-S node), one thread, BFS inside the subtree
   void run_subtree(int k, const PNode& root) {
     std::vector<PNode> cur{root}, next;
+    std::vector<NodePlan> plans;
     for (int L = S; L < M; ++L) {
       next.assign(cur.size() * 4, PNode{0, 0, 0.0, 0.0});
-      for (size_t i = 0; i < cur.size(); ++i) do_node(cur[i], &next[4 * i], L & 1);
+      plans.assign(cur.size(), NodePlan());
+      for (size_t i = 0; i < cur.size(); ++i) classify(cur[i], L & 1, plans[i]);
       if (failed.load()) return;
       build_bits(sub[k][L - S], root.s, root.e, 1);
       sub_ready[k].store(L - S + 1, std::memory_order_release);     // levels S .. L of this subtree are published
+      for (size_t i = 0; i < cur.size(); ++i) scatter(cur[i], &next[4 * i], L & 1, plans[i]);
       cur.swap(next);
       std::copy(cur.begin(), cur.end(), level_nodes[L + 1].begin() + (size_t)k * cur.size());
     }
@@ -684,19 +707,28 @@ struct Partitioner {
       level_nodes[L] = cur;
       next.assign(cur.size() * 4, PNode{0, 0, 0.0, 0.0});
       const int b = L & 1;
-      // big nodes one after the other (all threads inside), the rest in parallel
+      // big nodes one after the other (all threads inside), the rest in parallel; the level's bit planes are
+      // published between the two passes, so the RNG replay does not wait for the row moves
       std::vector<int64_t> small;
+      std::vector<NodePlan> plans(cur.size());
       for (size_t i = 0; i < cur.size(); ++i) {
-        if (cur[i].e - cur[i].s >= BIG) do_node(cur[i], &next[4 * i], b);
+        if (cur[i].e - cur[i].s >= BIG) classify(cur[i], b, plans[i]);
         else small.push_back((int64_t)i);
       }
       run_parallel(nthreads, (int64_t)small.size(), [&](int64_t k) {
         const int64_t i = small[k];
-        do_node(cur[i], &next[4 * i], b);
+        classify(cur[i], b, plans[i]);
       });
       if (failed.load()) break;
       build_bits(lv[L], 0, N, nthreads);
       ready.store(L + 1, std::memory_order_release);
+      trace.mark("partition: level published", L);
+      for (size_t i = 0; i < cur.size(); ++i)
+        if (cur[i].e - cur[i].s >= BIG) scatter(cur[i], &next[4 * i], b, plans[i]);
+      run_parallel(nthreads, (int64_t)small.size(), [&](int64_t k) {
+        const int64_t i = small[k];
+        scatter(cur[i], &next[4 * i], b, plans[i]);
+      });
       trace.mark("partition: level done", L);
       cur.swap(next);
     }
