@@ -1004,6 +1004,7 @@ void setup_partitioner(Partitioner& P, Builder& B, int64_t N, int M) {
   }
   P.code = B.code;
   P.S = std::min(2, (int)M);
+  if (const char* e = std::getenv("MRA_BUILD_S")) P.S = std::max(1, std::min((int)M, std::atoi(e)));
   P.lv.resize(P.S);
   const int nsub = P.S < M ? 1 << (2 * P.S) : 0;
   P.sub.assign(nsub, std::vector<LevelBits>(M - P.S));
