@@ -121,9 +121,23 @@ def dgemm_peak_tflops(torch, n=6144):
     return 2.0 * n ** 3 / best * 1e-9
 
 
+def blas_all_threads():
+    """The CPU legs use every host thread BLAS/LAPACK can take: torchrun exports OMP_NUM_THREADS=1, which would
+    otherwise pin NumPy's BLAS to one thread.  Returns the thread count now in effect."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=n)
+        got = [int(p.get("num_threads", 1)) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(got) if got else n
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", n))
+
+
 def cpu_baseline(r, M, family, l, sig, R, frac_obs, n_full, steps=1, warmup=0):
     """Oracle port on a bounded sample; returns (evals/s at the full size, description, cores, s/step)."""
     from oracle.mra_oracle import mra_oracle
+    blas_all_threads()
     locs, obs = make_inputs(SAMPLE_GRID, frac_obs, seed=4)
     times = []
     for it in range(warmup + steps):
@@ -145,7 +159,7 @@ def run_reference(args, rank, world):
     N = n * n
     t0 = time.time()
     evals, locs_s, per = cpu_baseline(r, M, family, l, sig, R, frac, N, steps=args.steps, warmup=args.warmup)
-    cores = os.cpu_count()
+    cores = blas_all_threads()
     sample = ("oracle/mra_oracle.py (NumPy/LAPACK restatement of pyMRA, gc.collect not called) on a %dx%d grid, "
               "r0=%d: one level-3 subtree of the workload, same leaf sizes; %.0f locs/s scaled by 1/N to evals/s "
               "(optimistic for the CPU twice over: the full tree is 3 levels deeper, and on these very inputs the "
@@ -304,7 +318,7 @@ def run_ours(args, rank, world, local_rank):
     cb = None
     if not args.no_cpu_baseline and world == 1:
         evals, locs_s, per = cpu_baseline(r, Mreq, family, l, sig, R, frac, N)
-        cb = {"value": evals, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+        cb = {"value": evals, "unit": "evals/s", "cores": blas_all_threads(), "kind": "port",
               "sample": "oracle/mra_oracle.py on a %dx%d grid, r0=%d (one level-3 subtree of the workload, same leaf "
                         "sizes): %.1f s, %.0f locs/s, scaled by 1/N; the unmodified reference is 9.4-13x slower than "
                         "this port on the same inputs (profiles/r03_reference_vs_port_build_container.jsonl)"
