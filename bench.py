@@ -152,6 +152,38 @@ def cpu_baseline(r, M, family, l, sig, R, frac_obs, n_full, steps=1, warmup=0):
     return locs_per_s / n_full, locs_per_s, per
 
 
+def _oracle_proc(job):
+    """One process of the multiprocess CPU leg (spawned): the oracle port on its own sample subtree."""
+    grid, frac, seed, r, M, family, l, sig, R, threads = job
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=threads)
+    except Exception:
+        pass
+    from oracle.mra_oracle import mra_oracle
+    locs, obs = make_inputs(grid, frac, seed=seed)
+    np.random.seed(5 + seed)
+    t0 = time.time()
+    mra_oracle(locs, r, family, l, sig, obs, R, M=M)
+    return time.time() - t0, len(locs)
+
+
+def cpu_baseline_multiprocess(r, M, family, l, sig, R, frac_obs, n_full, procs=4):
+    """The reference's multiprocess subtree mode (pyMRA/MRANode.py:90-104: one forked process per child at
+    critDepth, J = 4 children) restated for the port: `procs` processes, one sample subtree each, the BLAS
+    threads divided between them.  Returns (evals/s at the full size, locs/s, procs, threads per process)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = max(1, min(procs, cores))
+    threads = max(1, cores // procs)
+    jobs = [(SAMPLE_GRID, frac_obs, 4 + k, r, M, family, l, sig, R, threads) for k in range(procs)]
+    with mp.get_context("spawn").Pool(procs) as pool:
+        res = pool.map(_oracle_proc, jobs)
+    # the processes run side by side: aggregate rate = sum of the per-process rates
+    locs_per_s = float(sum(n / dt for dt, n in res))
+    return locs_per_s / n_full, locs_per_s, procs, threads
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -160,8 +192,19 @@ def run_reference(args, rank, world):
     t0 = time.time()
     evals, locs_s, per = cpu_baseline(r, M, family, l, sig, R, frac, N, steps=args.steps, warmup=args.warmup)
     cores = blas_all_threads()
+    serial = {"evals_per_s": evals, "locs_per_s": locs_s, "s_per_sample": per, "blas_threads": cores}
+    modes = {"serial": serial}
+    try:      # the reference's multiprocess subtree mode; the better of the two modes is the line's value
+        mp_evals, mp_locs_s, procs, threads = cpu_baseline_multiprocess(r, M, family, l, sig, R, frac, N)
+        modes["multiprocess"] = {"evals_per_s": mp_evals, "locs_per_s": mp_locs_s, "processes": procs,
+                                 "blas_threads_per_process": threads}
+        if mp_evals > evals:
+            evals, locs_s = mp_evals, mp_locs_s
+    except Exception as e:      # never lose the serial number over the extra mode
+        modes["multiprocess"] = {"error": repr(e)}
     sample = ("oracle/mra_oracle.py (NumPy/LAPACK restatement of pyMRA, gc.collect not called) on a %dx%d grid, "
-              "r0=%d: one level-3 subtree of the workload, same leaf sizes; %.0f locs/s scaled by 1/N to evals/s "
+              "r0=%d: one level-3 subtree of the workload, same leaf sizes, serial and as 4 processes side by side "
+              "(the reference's fork-per-child mode); best mode %.0f locs/s scaled by 1/N to evals/s "
               "(optimistic for the CPU twice over: the full tree is 3 levels deeper, and on these very inputs the "
               "unmodified reference takes 9.4x (gc.collect stubbed) to 13x (as is) longer than this port -- "
               "profiles/r03_reference_vs_port_build_container.jsonl)" % (SAMPLE_GRID, SAMPLE_GRID, r, locs_s))
@@ -172,7 +215,8 @@ def run_reference(args, rank, world):
             "config": {"workload": args.workload, "grid": [n, n], "n_locs": N, "r0": r, "M_requested": M,
                        "cov": family, "l": l, "R": R, "frac_obs": frac},
             "predict_locations_per_s": locs_s,
-            "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": sample, "modes": modes},
             "e2e": {"value": evals, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
@@ -318,9 +362,20 @@ def run_ours(args, rank, world, local_rank):
     cb = None
     if not args.no_cpu_baseline and world == 1:
         evals, locs_s, per = cpu_baseline(r, Mreq, family, l, sig, R, frac, N)
-        cb = {"value": evals, "unit": "evals/s", "cores": blas_all_threads(), "kind": "port",
+        modes = {"serial": {"evals_per_s": evals, "locs_per_s": locs_s, "s_per_sample": per,
+                            "blas_threads": blas_all_threads()}}
+        try:
+            mp_evals, mp_locs_s, procs, threads = cpu_baseline_multiprocess(r, Mreq, family, l, sig, R, frac, N)
+            modes["multiprocess"] = {"evals_per_s": mp_evals, "locs_per_s": mp_locs_s, "processes": procs,
+                                     "blas_threads_per_process": threads}
+            if mp_evals > evals:
+                evals, locs_s = mp_evals, mp_locs_s
+        except Exception as e:
+            modes["multiprocess"] = {"error": repr(e)}
+        cb = {"value": evals, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port", "modes": modes,
               "sample": "oracle/mra_oracle.py on a %dx%d grid, r0=%d (one level-3 subtree of the workload, same leaf "
-                        "sizes): %.1f s, %.0f locs/s, scaled by 1/N; the unmodified reference is 9.4-13x slower than "
+                        "sizes), serial %.1f s per sample and as 4 processes side by side; best mode %.0f locs/s, "
+                        "scaled by 1/N; the unmodified reference is 9.4-13x slower than "
                         "this port on the same inputs (profiles/r03_reference_vs_port_build_container.jsonl)"
                         % (SAMPLE_GRID, SAMPLE_GRID, r, per, locs_s)}
 
