@@ -38,6 +38,8 @@ WORKLOADS = {
     "tiny": (250, 64, 10, "matern32", 0.3, 1.0, 1e-2, 0.4),
 }
 SAMPLE_GRID = 250   # cpu baseline sample: one level-3 subtree of cfg5 (same r0, same leaf sizes)
+if os.environ.get("MRA_BENCH_SAMPLE_GRID"):      # tests/test_bench_contract.py shrinks the sample
+    SAMPLE_GRID = int(os.environ["MRA_BENCH_SAMPLE_GRID"])
 
 
 def make_inputs(n, frac_obs, seed=3):
