@@ -189,6 +189,9 @@ int mra_stream_end_async(mra_handle *h, void *stream);
  * mra_run_likelihood_local_async; the caller all-reduces them and calls mra_run_likelihood_top_async. */
 int mra_stream_my_parts(const mra_handle *h, int32_t *mask);
 int mra_stream_end_local_async(mra_handle *h, void *stream, double *dev_summary);
+/* Brings the complete, final knot table to the device (a sharded streamed pass uploaded only the knots of the
+ * parts this rank ran; plain passes such as a later re-fit factor every replicated top node). */
+int mra_stream_sync_knots(mra_handle *h, void *stream, const int64_t *knot_rows);
 
 /* Counters for bench.py: kernels launched by the last run_* call, and algorithmic FP64
  * flop of the last likelihood / predict pass as executed. */

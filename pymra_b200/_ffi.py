@@ -63,6 +63,7 @@ SIGNATURES = {
     "mra_stream_end_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mra_stream_my_parts": (C.c_int, [C.c_void_p, _p32]),
     "mra_stream_end_local_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mra_stream_sync_knots": (C.c_int, [C.c_void_p, C.c_void_p, _p64]),
     "mra_last_launches": (C.c_int, [C.c_void_p, _p64]),
     "mra_last_flops": (C.c_int, [C.c_void_p, _pd, _pd]),
     "mra_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

@@ -1298,6 +1298,24 @@ int mra_stream_end_async(mra_handle* h, void* stream) {
   return launch_likelihood_top(h, st, nullptr);     // shard_level == 0: only the final reduction
 }
 
+// After a streamed pass on a sharded handle the device has seen only the knots of the parts this rank ran; later
+// plain passes (refit) factor every replicated top node, so the complete knot table is brought over once the
+// build has ended (the caller's knot_rows is final by then).
+int mra_stream_sync_knots(mra_handle* h, void* stream, const int64_t* knot_rows) {
+  if (!h || !knot_rows) return MRA_ERR_ARG;
+  if (!h->uploaded) return fail(h, MRA_ERR_STATE, "mra_upload_data must be called first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  if (h->knot_rows.empty()) return MRA_OK;
+  int rc = upload_knot_ranges(h, st, knot_rows, std::vector<Range>{Range{0, (int)h->knot_rows.size()}});
+  if (rc) return rc;
+  for (const int2& gn : h->gather_node) {
+    rc = upload_knot_ranges(h, st, knot_rows, std::vector<Range>{Range{(int)h->knot_off[gn.x], h->r}}, gn);
+    if (rc) return rc;
+  }
+  return MRA_OK;
+}
+
 int mra_stream_end_local_async(mra_handle* h, void* stream, double* dev_summary) {
   if (!h) return MRA_ERR_ARG;
   if (h->shard_level < 1 || h->shard_level > 2)

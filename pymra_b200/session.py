@@ -176,6 +176,12 @@ class DeviceSession(object):
         self.stream_end_local()
         dist.all_reduce(self.summary, group=self.group)       # disjoint slots: the sum is exact
         self.likelihood_top_async()
+        self.sync_knots()
+
+    def sync_knots(self):
+        """Sharded streamed pass: the knots of the parts other ranks ran reach this device now (the build has
+        ended, the table is final) -- a later plain pass (refit) factors every replicated top node."""
+        self.check(self.lib.mra_stream_sync_knots(self.h, self.stream(), self._knots_ptr()))
 
     def fetch_likelihood(self):
         out = (C.c_double * 2)()

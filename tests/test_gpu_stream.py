@@ -138,5 +138,12 @@ def test_emulated_shards_stream_their_parts(world):
     got = finish(got_total)
     assert got[0] == want[0] and all(l == got[0][0] for l in got[0])
     assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    # a plain pass after the streamed one (what refit() runs) needs the knots of every replicated top node
+    for s in sess:
+        s.sync_knots()
+        s.likelihood_local_async()
+    assert torch.equal(torch.stack([s.summary for s in sess]).sum(0), want_total)
+    again = finish(want_total.clone())
+    assert again[0] == want[0] and np.array_equal(again[1], want[1]) and np.array_equal(again[2], want[2])
     for s in sess:
         s.close()
