@@ -186,39 +186,100 @@ def cpu_baseline_multiprocess(r, M, family, l, sig, R, frac_obs, n_full, procs=4
     return locs_per_s / n_full, locs_per_s, procs, threads
 
 
+def _oracle_fork_job(job, conn):
+    """Fresh interpreter (spawned): the oracle port on ONE sample tree in the reference's real multiprocess mode,
+    critDepth = 0 -- the root forks one process per child subtree and receives the pickled child nodes
+    (pyMRA/MRANode.py:90-104, 114-115)."""
+    grid, frac, seed, r, M, family, l, sig, R = job
+    from oracle.mra_oracle import mra_oracle
+    locs, obs = make_inputs(grid, frac, seed=seed)
+    np.random.seed(5)
+    t0 = time.time()
+    mra_oracle(locs, r, family, l, sig, obs, R, M=M, critDepth=0, processes=True)
+    conn.send((time.time() - t0, len(locs)))
+    conn.close()
+
+
+def cpu_baseline_fork(r, M, family, l, sig, R, frac_obs, n_full):
+    """Returns (evals/s at the full size, locs/s, seconds per sample) of the port's real fork mode."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    rx, tx = ctx.Pipe(duplex=False)
+    p = ctx.Process(target=_oracle_fork_job, args=((SAMPLE_GRID, frac_obs, 4, r, M, family, l, sig, R), tx))
+    p.start()
+    tx.close()
+    if not rx.poll(900):
+        p.terminate()
+        raise RuntimeError("fork-mode CPU leg timed out")
+    dt, n = rx.recv()
+    p.join()
+    return n / dt / n_full, n / dt, dt
+
+
+def cpu_legs(r, M, family, l, sig, R, frac, N, steps=1, warmup=0):
+    """All CPU modes of the bounded sample; returns (best evals/s, best locs/s, seconds per serial sample, modes)."""
+    evals, locs_s, per = cpu_baseline(r, M, family, l, sig, R, frac, N, steps=steps, warmup=warmup)
+    modes = {"serial": {"evals_per_s": evals, "locs_per_s": locs_s, "s_per_sample": per,
+                        "blas_threads": blas_all_threads()}}
+    try:      # the reference's multiprocess subtree mode on the same single tree (critDepth = 0, real forks)
+        f_evals, f_locs_s, f_per = cpu_baseline_fork(r, M, family, l, sig, R, frac, N)
+        modes["fork_critDepth0"] = {"evals_per_s": f_evals, "locs_per_s": f_locs_s, "s_per_sample": f_per,
+                                    "processes": 4}
+        if f_evals > evals:
+            evals, locs_s = f_evals, f_locs_s
+    except Exception as e:
+        modes["fork_critDepth0"] = {"error": repr(e)}
+    try:      # four independent sample trees side by side: an upper bound of what 4 processes can deliver
+        mp_evals, mp_locs_s, procs, threads = cpu_baseline_multiprocess(r, M, family, l, sig, R, frac, N)
+        modes["side_by_side"] = {"evals_per_s": mp_evals, "locs_per_s": mp_locs_s, "processes": procs,
+                                 "blas_threads_per_process": threads}
+        if mp_evals > evals:
+            evals, locs_s = mp_evals, mp_locs_s
+    except Exception as e:      # never lose the serial number over the extra modes
+        modes["side_by_side"] = {"error": repr(e)}
+    return evals, locs_s, per, modes
+
+
+def full_size_check(workload, serial_locs_per_s):
+    """Measured full-size port time (profiles/r04_fullsize_port_times.json, from tools/parity_fullsize.py on a GPU
+    box's host) over the time the 1/N extrapolation of this run's serial sample predicts for the same size."""
+    path = os.path.join(ROOT, "profiles", "r04_fullsize_port_times.json")
+    if not os.path.exists(path):
+        return None
+    rec = json.load(open(path)).get(workload)
+    if not rec:
+        return None
+    extrap = rec["n_locs"] / serial_locs_per_s
+    return {"measured_port_s": rec["port_s"], "measured_on_cores": rec["host_cores"], "extrapolated_s": extrap,
+            "measured_over_extrapolated": rec["port_s"] / extrap,
+            "note": "ratio > 1: the 1/N extrapolation of the sample flatters the CPU (the full tree is deeper)"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     n, r, M, family, l, sig, R, frac = WORKLOADS[args.workload]
     N = n * n
     t0 = time.time()
-    evals, locs_s, per = cpu_baseline(r, M, family, l, sig, R, frac, N, steps=args.steps, warmup=args.warmup)
-    cores = blas_all_threads()
-    serial = {"evals_per_s": evals, "locs_per_s": locs_s, "s_per_sample": per, "blas_threads": cores}
-    modes = {"serial": serial}
-    try:      # the reference's multiprocess subtree mode; the better of the two modes is the line's value
-        mp_evals, mp_locs_s, procs, threads = cpu_baseline_multiprocess(r, M, family, l, sig, R, frac, N)
-        modes["multiprocess"] = {"evals_per_s": mp_evals, "locs_per_s": mp_locs_s, "processes": procs,
-                                 "blas_threads_per_process": threads}
-        if mp_evals > evals:
-            evals, locs_s = mp_evals, mp_locs_s
-    except Exception as e:      # never lose the serial number over the extra mode
-        modes["multiprocess"] = {"error": repr(e)}
+    evals, locs_s, per, modes = cpu_legs(r, M, family, l, sig, R, frac, N, steps=args.steps, warmup=args.warmup)
+    fsc = full_size_check(args.workload, modes["serial"]["locs_per_s"])
     sample = ("oracle/mra_oracle.py (NumPy/LAPACK restatement of pyMRA, gc.collect not called) on a %dx%d grid, "
-              "r0=%d: one level-3 subtree of the workload, same leaf sizes, serial and as 4 processes side by side "
-              "(the reference's fork-per-child mode); best mode %.0f locs/s scaled by 1/N to evals/s "
-              "(optimistic for the CPU twice over: the full tree is 3 levels deeper, and on these very inputs the "
-              "unmodified reference takes 9.4x (gc.collect stubbed) to 13x (as is) longer than this port -- "
+              "r0=%d: one level-3 subtree of the workload, same leaf sizes; modes: serial (BLAS on all cores), the "
+              "reference's fork-per-child mode on that tree (critDepth=0, real forks), and 4 sample trees side by side; "
+              "best mode %.0f locs/s scaled by 1/N to evals/s (an ESTIMATE that flatters the CPU: the full tree is 3 "
+              "levels deeper -- see full_size_check -- and on these very inputs the unmodified reference takes 9.4x "
+              "(gc.collect stubbed) to 13x (as is) longer than this port, "
               "profiles/r03_reference_vs_port_build_container.jsonl)" % (SAMPLE_GRID, SAMPLE_GRID, r, locs_s))
     line = {"impl": "reference", "metric": "getLikelihood() evals/sec and predict() locations/sec at n=4M",
             "value": evals, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "ms_per_step": 1e3 / evals, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "same_config": False, "extrapolated": True,
+            "sample_grid": [SAMPLE_GRID, SAMPLE_GRID], "sample_s_per_step": per,
             "config": {"workload": args.workload, "grid": [n, n], "n_locs": N, "r0": r, "M_requested": M,
                        "cov": family, "l": l, "R": R, "frac_obs": frac},
             "predict_locations_per_s": locs_s,
             "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": sample, "modes": modes},
+                             "sample": sample, "modes": modes, "full_size_check": fsc},
             "e2e": {"value": evals, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
@@ -344,40 +405,57 @@ def run_ours(args, rank, world, local_rank):
         kern[name] = {"ms_per_step": ms, "launches_per_step": p["launches"] / args.steps,
                       "tflops": p["flops"] / (ms * 1e-3) * 1e-12 if ms > 0 else 0.0,
                       "gbs": p["bytes"] / (ms * 1e-3) * 1e-9 if ms > 0 else 0.0}
-    top = max(kern, key=lambda k: kern[k]["ms_per_step"])
-    traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    ridge = peak * 1e3 / hbm_peak            # flop per byte where the two roofs meet
+    tj = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic_%s.json" % args.workload)
     if world == 1 and os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if top in tj and tj[top]["launches"]:
-            traffic = tj[top]["dram_bytes"] / tj[top]["launches"]
-    roofline = {"kernel": top, "bound": "tensor", "achieved": kern[top]["tflops"], "peak": peak,
-                "unit": "TFLOP/s", "frac": kern[top]["tflops"] / peak, "traffic": traffic,
-                "traffic_source": "profiles/ncu_traffic_%s.json (dram__bytes_read+write.sum per launch, ncu --set full)" % args.workload
-                if traffic is not None else None,
-                "peak_source": "cuBLAS DGEMM (torch.matmul f64, n=6144) measured in this run; "
-                               "MEASURED_PEAKS.json has no FP64 entry",
-                "share_of_step": kern[top]["ms_per_step"] / (total_ms / args.steps),
-                "whole_step_tflops": (f_lik + f_pred) / (total_ms / args.steps * 1e-3) * 1e-12}
+
+    def roof(name):
+        k = kern[name]
+        raw = prof[name]
+        intensity = raw["flops"] / raw["bytes"] if raw["bytes"] > 0 else float("inf")
+        traffic = None      # DRAM bytes per launch from the committed ncu --set full capture
+        if name in tj and tj[name]["launches"]:
+            traffic = tj[name]["dram_bytes"] / tj[name]["launches"]
+        out = {"kernel": name, "share_of_step": k["ms_per_step"] / (total_ms / args.steps),
+               "ms_per_step": k["ms_per_step"], "launches_per_step": k["launches_per_step"],
+               "algorithmic_flop_per_byte": intensity, "traffic": traffic,
+               "traffic_source": "profiles/ncu_traffic_%s.json (dram__bytes_read+write.sum per launch, ncu --set full)"
+               % args.workload if traffic is not None else None}
+        if intensity >= ridge:
+            out.update(bound="tensor", achieved=k["tflops"], peak=peak, unit="TFLOP/s", frac=k["tflops"] / peak,
+                       peak_source="cuBLAS DGEMM (torch.matmul f64, n=6144) measured in this run; "
+                                   "MEASURED_PEAKS.json has no FP64 entry")
+        else:
+            out.update(bound="hbm", achieved=k["gbs"], peak=hbm_peak, unit="GB/s", frac=k["gbs"] / hbm_peak,
+                       peak_source=hbm_src, tensor_tflops=k["tflops"], tensor_frac=k["tflops"] / peak)
+        return out
+
+    order = sorted(kern, key=lambda k: -kern[k]["ms_per_step"])
+    top = order[0]
+    roofline = roof(top)
+    roofline["ridge_flop_per_byte"] = ridge
+    roofline["whole_step_tflops"] = (f_lik + f_pred) / (total_ms / args.steps * 1e-3) * 1e-12
+    roofline["whole_step_frac"] = roofline["whole_step_tflops"] / peak
+    roofline["others"] = [roof(k) for k in order[1:4]]       # the next heaviest kernel families, same accounting
 
     # ---- CPU baseline (rank 0, bounded sample)
     cb = None
     if not args.no_cpu_baseline and world == 1:
-        evals, locs_s, per = cpu_baseline(r, Mreq, family, l, sig, R, frac, N)
-        modes = {"serial": {"evals_per_s": evals, "locs_per_s": locs_s, "s_per_sample": per,
-                            "blas_threads": blas_all_threads()}}
-        try:
-            mp_evals, mp_locs_s, procs, threads = cpu_baseline_multiprocess(r, Mreq, family, l, sig, R, frac, N)
-            modes["multiprocess"] = {"evals_per_s": mp_evals, "locs_per_s": mp_locs_s, "processes": procs,
-                                     "blas_threads_per_process": threads}
-            if mp_evals > evals:
-                evals, locs_s = mp_evals, mp_locs_s
-        except Exception as e:
-            modes["multiprocess"] = {"error": repr(e)}
+        evals, locs_s, per, modes = cpu_legs(r, Mreq, family, l, sig, R, frac, N)
         cb = {"value": evals, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port", "modes": modes,
+              "full_size_check": full_size_check(args.workload, modes["serial"]["locs_per_s"]),
               "sample": "oracle/mra_oracle.py on a %dx%d grid, r0=%d (one level-3 subtree of the workload, same leaf "
-                        "sizes), serial %.1f s per sample and as 4 processes side by side; best mode %.0f locs/s, "
-                        "scaled by 1/N; the unmodified reference is 9.4-13x slower than "
+                        "sizes): serial %.1f s per sample, the reference's fork-per-child mode (critDepth=0) on the same "
+                        "tree, and 4 sample trees side by side; best mode %.0f locs/s, scaled by 1/N (an estimate, see "
+                        "full_size_check); the unmodified reference is 9.4-13x slower than "
                         "this port on the same inputs (profiles/r03_reference_vs_port_build_container.jsonl)"
                         % (SAMPLE_GRID, SAMPLE_GRID, r, per, locs_s)}
 

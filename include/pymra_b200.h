@@ -34,6 +34,12 @@ enum mra_status {
   MRA_BUILD_UNSUPPORTED = 1 /* mra_build_structure_2d met a node outside its fast path (not an error) */
 };
 
+/* Conditions that do not fail a pass but are worth knowing (mra_last_warnings). */
+enum mra_warning {
+  MRA_WARN_NEGATIVE_VARIANCE = 2 /* a predictive variance fell below -1e-12 C(0) by cancellation and was clamped to 0;
+                                    the reference's sum-of-squares form (MRANode.py:504-511) cannot go negative */
+};
+
 enum mra_cov_family {      /* pyMRA/MRATools.py */
   MRA_COV_EXP = 0,         /* ExpCovFun  :265-269   exp(-D/l)                          */
   MRA_COV_MATERN32 = 1,    /* Matern32   :289-293   sig*(1+sqrt(3)D/l)*exp(-sqrt(3)D/l) */
@@ -192,6 +198,10 @@ int mra_stream_end_local_async(mra_handle *h, void *stream, double *dev_summary)
 /* Brings the complete, final knot table to the device (a sharded streamed pass uploaded only the knots of the
  * parts this rank ran; plain passes such as a later re-fit factor every replicated top node). */
 int mra_stream_sync_knots(mra_handle *h, void *stream, const int64_t *knot_rows);
+
+/* Bit mask of mra_warning conditions seen by the passes since the last likelihood pass started; updated when a
+ * pass's status is read back (mra_fetch_likelihood, mra_run_likelihood, mra_run_predict). */
+int mra_last_warnings(const mra_handle *h, int32_t *flags);
 
 /* Counters for bench.py: kernels launched by the last run_* call, and algorithmic FP64
  * flop of the last likelihood / predict pass as executed. */

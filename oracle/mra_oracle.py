@@ -285,15 +285,36 @@ def _build(ctx, parent, ID, rows, nk_local, levels_left):
         state = np.random.get_state() if fork else None
         is_rest = np.zeros(node.N, dtype=bool)
         is_rest[rest] = True
-        for j, part in enumerate(parts):
-            chID = ID + str(j + 1)
-            node.inds[chID] = part
+        if fork and ctx.processes:
+            # MRANode.py:90-104 for real: one forked process per child, every child starts from the parent's RNG
+            # state (fork copies it), the finished child Node comes back pickled through a pipe
+            import multiprocessing as mp
+            mpc = mp.get_context("fork")
+            jobs = []
+            for j, part in enumerate(parts):
+                chID = ID + str(j + 1)
+                node.inds[chID] = part
+                rx, tx = mpc.Pipe(duplex=False)
+                p = mpc.Process(target=_forked_child, args=(ctx, node, chID, rows[part], np.flatnonzero(is_rest[part]),
+                                                            levels_left - 1, tx, len(parts)))
+                p.start()
+                tx.close()
+                jobs.append((p, rx))
+            for p, rx in jobs:
+                ch = rx.recv()
+                ch.parent = node
+                node.children.append(ch)
+                p.join()
+        else:
+            for j, part in enumerate(parts):
+                chID = ID + str(j + 1)
+                node.inds[chID] = part
+                if fork:
+                    np.random.set_state(state)
+                ch = _build(ctx, node, chID, rows[part], np.flatnonzero(is_rest[part]), levels_left - 1)
+                node.children.append(ch)
             if fork:
                 np.random.set_state(state)
-            ch = _build(ctx, node, chID, rows[part], np.flatnonzero(is_rest[part]), levels_left - 1)
-            node.children.append(ch)
-        if fork:
-            np.random.set_state(state)
     _posterior(ctx, node)
     if ctx.record is not None:
         ctx.record.append(dict(ID=ID, rows=rows, kInds=node.kInds, leaf=node.leaf, d=node.d, u=node.u))
@@ -303,11 +324,28 @@ def _build(ctx, parent, ID, rows, nk_local, levels_left):
     return node
 
 
+def _forked_child(ctx, parent, chID, rows, nk_local, levels_left, pipe, n_siblings):
+    """Body of one forked child process (MRANode.py:92-93, 114-115): builds the subtree and pipes the Node back."""
+    try:
+        from threadpoolctl import threadpool_limits
+        import os
+        threadpool_limits(limits=max(1, (os.cpu_count() or 1) // max(1, n_siblings)))
+    except Exception:
+        pass
+    ctx.record = None                      # per-node records do not cross the process boundary
+    ch = _build(ctx, parent, chID, rows, nk_local, levels_left)
+    ch.parent = None                       # the reference pickles the parent chain too; the slim Node is kinder to the CPU
+    pipe.send(ch)
+    pipe.close()
+
+
 def mra_oracle(locs, r, family, l, sig, obs, R, M=-1, J=-1, critDepth=-1, logdet="slogdet",
-               record=False):
+               record=False, processes=False):
     """Restatement of MRATree(locs, r, cov, obs, R, M, J, critDepth) + getLikelihood() + predict().
 
-    Consumes the global NumPy RNG exactly like the reference.  Returns a dict with
+    Consumes the global NumPy RNG exactly like the reference.  processes=True runs the children of the
+    critDepth node as forked processes like the reference (default: same RNG semantics, one process).
+    Returns a dict with
     lik (= root.d + root.u, MRATree.py:82-84), mean, sd (MRATree.py:90-94), M, J and,
     if record, the node list (DFS post-order) with global rows and local knot ids.
     """
@@ -322,6 +360,7 @@ def mra_oracle(locs, r, family, l, sig, obs, R, M=-1, J=-1, critDepth=-1, logdet
     ctx.cov = make_cov(family, l, sig)
     ctx.logdet = logdet
     ctx.record = [] if record else None
+    ctx.processes = bool(processes)        # True: really fork one process per child at critDepth (MRANode.py:90-104)
     root = _build(ctx, None, "r", np.arange(N, dtype=np.int64), np.arange(N, dtype=np.int64), M)
     out = dict(lik=float(root.d + root.u), d=float(root.d), u=float(root.u),
                mean=np.asarray(root.mean).reshape(-1), sd=np.sqrt(root.var), M=M, J=J,

@@ -20,6 +20,7 @@ import weakref
 
 import numpy as np
 
+from . import _ffi
 from .covariance import introspect
 from .session import DeviceSession
 from .structure import StreamBuild, build_structure
@@ -72,6 +73,14 @@ class _Root(object):
         return t
 
     @property
+    def B(self):
+        """The root's prior basis cov(locs, knots) (MRANode.py:384; no ancestors to condition on), evaluated with the
+        caller's closure on first use -- what callers of the reference read from tree.root.B."""
+        t = self._tree
+        X = np.asarray(t.locs, dtype=np.float64).reshape(t._N, t.d)
+        return np.matrix(t._cov_closure(X, X[self.kInds]))
+
+    @property
     def mean(self):
         return self._tree._moments()[0]
 
@@ -97,14 +106,15 @@ class MRATree(object):
             logger.warning("The number of resolutions M=%d you requested is to large for your grid. "
                            "Setting M:=%d" % clamped)
         self.M, self.J = M, J
-        if not isinstance(R, float):
-            raise TypeError("R (me_scale) must be a Python/NumPy float; the reference's matrix-valued R "
+        if isinstance(R, bool) or not isinstance(R, (int, float, np.integer, np.floating)):
+            raise TypeError("R (me_scale) must be a real scalar; the reference's matrix-valued R "
                             "path is broken (MRANode.py:421) and is not accelerated")
         obs_arr = np.asarray(obs, dtype=np.float64)
         if obs_arr.shape != (N, 1):
             raise ValueError("obs must have shape (N, 1) (the reference wraps it in np.matrix, MRATree.py:61)")
         self._obs_ref = obs
         self._obs_inds = None
+        self._cov_closure = cov
         self._cov = introspect(cov, self.d)
         self._R = float(R)
         logger.debug("r: %d, \tJ: %d,\tM: %d" % (self.r, self.J, self.M))
@@ -130,7 +140,7 @@ class MRATree(object):
                     box.append((torch.from_numpy(locs_c).to(dev, non_blocking=True),
                                 torch.from_numpy(np.ascontiguousarray(obs_arr).reshape(-1)).to(dev, non_blocking=True)))
                 self._structure = build_structure_group(locs_c, r, M, J, critDepth, None if group is True else group,
-                                                        async_start=early_h2d)
+                                                        async_start=early_h2d, device=device)
                 staged = box[0] if box else None
             else:
                 self._structure = build_structure(locs_c, r, M, J, critDepth)
@@ -167,7 +177,7 @@ class MRATree(object):
             world, rank = dist.get_world_size(g), dist.get_rank(g)
             if world > 16 or len(locs_c) < 65536 or M < 1 or M > 12:    # deterministic on every rank
                 return
-            sb = GroupStreamBuild(locs_c, r, M, J, critDepth, g)
+            sb = GroupStreamBuild(locs_c, r, M, J, critDepth, g, device=device)
         if not sb.started:
             return
         session = None
@@ -205,6 +215,7 @@ class MRATree(object):
             if streamable:
                 session.stream_end()
             else:                         # built (RNG advanced) but not streamable: plain passes on the finished tree
+                session.sync_knots()      # the session was set up at event 0, when only the root's knots were final
                 session.likelihood_async()
             self._structure = sb.structure
             self._session, session = session, None
@@ -238,6 +249,9 @@ class MRATree(object):
         if self._mom is None:
             t0 = time.perf_counter()
             mean, sd = self._session.predict()
+            if self._session.warnings() & _ffi.WARN_NEGATIVE_VARIANCE:
+                logger.warning("predict(): a predictive variance fell below -1e-12*C(0) by cancellation and was "
+                               "clamped to zero (the covariance is close to singular at this resolution)")
             if mean is None:            # sharded run with gather="root" on a non-root rank
                 self._mom = (None, None)
             else:
@@ -263,10 +277,11 @@ class MRATree(object):
         """Re-evaluate likelihood (and, lazily, predictions) for new covariance parameters / nugget
         on the SAME tree structure and device-resident data."""
         if cov is not None:
+            self._cov_closure = cov
             self._cov = introspect(cov, self.d)
         if R is not None:
-            if not isinstance(R, float):
-                raise TypeError("R must be a float")
+            if isinstance(R, bool) or not isinstance(R, (int, float, np.integer, np.floating)):
+                raise TypeError("R must be a real scalar")
             self._R = float(R)
         self._evaluate()
         self.root = _Root(self)

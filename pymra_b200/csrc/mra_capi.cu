@@ -45,7 +45,7 @@ struct Arena {
 
 struct Layout {
   size_t nodes, knot_rows, obs_rows, unobs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
-      mean, var, vnorm, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, ptiles, gather, chunks, ltiles, GTF, UTF, fold, VKL;
+      mean, var, vnorm, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, ptiles, pgroups, gather, chunks, ltiles, GTF, UTF, fold, VKL;
   size_t total;
 };
 
@@ -70,6 +70,11 @@ struct mra_handle {
   std::vector<int> gather_rows;                // row ids of the gathered tiles
   std::vector<int2> gather_node;               // (top node, first slot in gather_rows): r slots each
   std::vector<int> n_regular_tiles;            // per level: tiles of ptiles_at that are not gathered tiles
+  std::vector<std::vector<int4>> pgroups_at;   // per level: runs of <= PG consecutive regular tiles of a node (k_prior_groups)
+  std::vector<std::vector<int>> group_of_tile; // per level: regular tile -> its group
+  std::vector<size_t> pgroups_off;             // per level offsets (bytes) inside lay.pgroups
+  bool use_groups = true;
+  bool chol_mma = true;
   std::vector<int4> leaf_tiles;                // 64-row tiles of leaves / orphans (fused predict pass)
   std::vector<int4> fold_items;                // (node, ancestor level, row tile, column tile) of k_fold
   std::vector<int2> emit_chunks;               // row ranges whose results this rank emits
@@ -108,6 +113,7 @@ struct mra_handle {
   double R = 1.0;
   bool cov_set = false, R_set = false;
   int64_t launches = 0;
+  int warnings = 0;                            // MRA_WARN_* bits seen since the last likelihood pass started
   double flops_lik = 0, flops_pred = 0;
   // per-kernel profiling (CUDA events on the launching stream)
   bool profiling = false;
@@ -118,8 +124,8 @@ struct mra_handle {
   std::vector<std::string> kname;
   std::vector<double> kflops, kbytes;   // algorithmic work per launch-group, accumulated at plan time
   std::vector<double> kms;
-  const char* memo_name[16] = {};   // add_work: literal pointer -> kernel id
-  int memo_id[16] = {};
+  const char* memo_name[64] = {};   // add_work: literal pointer -> kernel id
+  int memo_id[64] = {};
   std::vector<int64_t> klaunch;
 };
 
@@ -154,6 +160,27 @@ int fail(mra_handle* h, int code, const std::string& msg) {
     if (e_ != cudaSuccess)                                                                       \
       return fail(h, MRA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
   } while (0)
+
+// Every entry point that touches the device selects the handle's device for its own duration and restores the
+// caller's current device on the way out (a handle on device k must not change PyTorch's current device).
+struct DevGuard {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t err = cudaSuccess;
+  explicit DevGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      changed = err == cudaSuccess;
+    }
+  }
+  ~DevGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+#define DEVICE_SCOPE(h)          \
+  DevGuard dev_guard_((h)->device); \
+  CU(dev_guard_.err)
 
 template <class T>
 T* at(mra_handle* h, size_t off) {
@@ -195,18 +222,21 @@ DevCtx make_ctx(mra_handle* h) {
   c.status = at<int>(h, L.status);
   c.cov = h->cov;
   c.R = h->R;
+  c.chol_mma = h->chol_mma ? 1 : 0;
   return c;
 }
 
 constexpr size_t GS = sizeof(GemmSmem);     // kernels with segmented products
 constexpr size_t GS1 = sizeof(GemmSmem1);   // single-segment kernels
-size_t smem_knot(int r) { return GS1 + sizeof(double) * ((size_t)r * (r + 1) + 3 * r + NT * 9) + sizeof(int) * r + 16; }
+size_t smem_knot(int r) { return GS1 + sizeof(double) * ((size_t)2 * r) + sizeof(int) * r + 16; }   // k_knot_gram
+size_t smem_cholinv(int n) {     // the larger of the two chol_inv_block variants
+  return sizeof(double) * std::max((size_t)n * (n + 1) + n + NT * 9 + 8, chol_mma_smem_doubles(n));
+}
 size_t smem_prior(int r) { return sizeof(GemmSmemT<2>) + sizeof(double) * ((size_t)2 * r + 2 * TB) + sizeof(int) * TB; }
+size_t smem_pgroups(int r) { return sizeof(PriorSmem) + sizeof(double) * ((size_t)2 * r + 2 * PG * TB); }
 size_t smem_gram() { return GS1 + sizeof(int) * 2 * TB; }
-size_t smem_chol(int max_obs) { return GS1 + sizeof(double) * ((size_t)TB * LDB + TB + NT * 9 + TB + ((max_obs + TB - 1) / TB) * TB); }
 size_t smem_solve() { return GS1; }
 size_t smem_plain() { return sizeof(GemmSmemT<4>); }   // k_assemble_A: up to 4 children per product
-size_t smem_factor(int r) { return GS1 + sizeof(double) * ((size_t)r * (r + 1) + r + NT * 9); }
 size_t smem_predict(int r) {
   int ldT = ((r + 15) / 16) * 16 + 4;
   return GS + sizeof(double) * ((size_t)(r > TB ? TB * ldT : 0) + 2 * TB) + sizeof(int) * MAX_LEVELS;
@@ -224,30 +254,70 @@ size_t smem_predict(int r) {
     }                                \
   } while (0)
 
+// Kernels whose tile columns are the r knots of a node are also instantiated for narrow tiles (NJ 8-column groups,
+// mra_gemm.cuh): r0 = 16 / 32 (BASELINE cfg4 / cfg3) run 64 x 16 / 64 x 32 tiles instead of zero-padded 64 x 64 ones.
+#define MRA_FOR_VEC_NJ(h, expr)                            \
+  do {                                                     \
+    if (((h)->r & 1) != 0) {                               \
+      constexpr int V_ = 1, J_ = 8;                        \
+      expr;                                                \
+    } else if ((h)->r <= 16) {                             \
+      constexpr int V_ = 2, J_ = 2;                        \
+      expr;                                                \
+    } else if ((h)->r <= 32) {                             \
+      constexpr int V_ = 2, J_ = 4;                        \
+      expr;                                                \
+    } else if ((h)->r <= 48) {                             \
+      constexpr int V_ = 2, J_ = 6;                        \
+      expr;                                                \
+    } else {                                               \
+      constexpr int V_ = 2, J_ = 8;                        \
+      expr;                                                \
+    }                                                      \
+  } while (0)
+
+template <int V_, int J_>
+cudaError_t configure_vec_nj(int r) {
+  cudaError_t e;
+#define SET_(k, bytes)                                                                         \
+  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));      \
+  if (e != cudaSuccess) return e
+  SET_((k_knot_gram<V_, J_>), smem_knot(r));
+  SET_((k_prior_tiles<V_, J_>), smem_prior(r));
+  if (V_ == 2) {
+    SET_((k_prior_groups<J_>), smem_pgroups(r));
+  }
+  SET_((k_node_gt<V_, J_>), GS1);
+  SET_((k_predict_fused<V_, J_>), smem_predict(r));
+#undef SET_
+  return cudaSuccess;
+}
+
 template <int V_>
 cudaError_t configure_vec(int r, int max_obs) {
   cudaError_t e;
 #define SET_(k, bytes)                                                                         \
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));      \
   if (e != cudaSuccess) return e
-  SET_(k_knot_factor<V_>, smem_knot(r));
-  SET_(k_prior_tiles<V_>, smem_prior(r));
+  SET_(k_knot_vkl<V_>, GS1);
   SET_(k_leaf_gram<V_>, smem_gram());
-  SET_(k_leaf_factor<V_>, smem_chol(max_obs));
+  SET_(k_leaf_upd<V_>, GS1);
+  SET_(k_leaf_trsm<V_>, GS1);
   SET_(k_leaf_solve_ut<V_>, smem_solve());
   SET_(k_leaf_solve_qt<V_>, smem_solve());
   SET_(k_assemble_A<V_>, smem_plain());
-  SET_(k_node_factor<V_>, smem_factor(r));
-  SET_(k_predict_fused<V_>, smem_predict(r));
+
   SET_(k_fold<V_>, GS1);
 #undef SET_
   return cudaSuccess;
 }
 
 int configure_kernels(mra_handle* h) {
-  if (smem_chol(h->max_leaf_obs) > 200 * 1024)
-    return fail(h, MRA_ERR_ARG, "a leaf has too many observations for this build");
   MRA_FOR_VEC(h, CU(configure_vec<V_>(h->r, h->max_leaf_obs)));
+  MRA_FOR_VEC_NJ(h, CU((configure_vec_nj<V_, J_>(h->r))));
+  CU(cudaFuncSetAttribute(k_knot_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cholinv(h->r)));
+  CU(cudaFuncSetAttribute(k_node_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cholinv(h->r)));
+  CU(cudaFuncSetAttribute(k_leaf_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cholinv(TB)));
   return MRA_OK;
 }
 
@@ -267,7 +337,7 @@ int kid(mra_handle* h, const std::string& name) {
 void add_work(mra_handle* h, const char* name, double flops, double bytes) {
   // called ~10x per node from mra_plan: memoise the id per literal (pointer identity) instead of a map lookup
   int id = -1;
-  const unsigned slot = (unsigned)((reinterpret_cast<uintptr_t>(name) >> 3) & 15);
+  const unsigned slot = (unsigned)((reinterpret_cast<uintptr_t>(name) >> 2) & 63);
   if (h->memo_name[slot] == name) id = h->memo_id[slot];
   if (id < 0) {
     id = kid(h, name);
@@ -318,12 +388,21 @@ int check_status(mra_handle* h, cudaStream_t st) {
   int flag = 0;
   CU(cudaMemcpyAsync(&flag, at<int>(h, h->lay.status), sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  if (flag != 0)
+  h->warnings |= flag & ~1;
+  if (flag & 1)
     return fail(h, MRA_ERR_NOT_SPD, "a Cholesky factorisation met a non-positive pivot (covariance not positive definite)");
   return MRA_OK;
 }
 
 using Range = mra_handle::Range;
+
+// elimination of the own level of `nn` nodes of level m: Cholesky factor + inverse (latency kernel), then GT (tiles)
+void node_factor(mra_handle* h, cudaStream_t st, const DevCtx& c, int m, const int* list, int nn) {
+  const int r = h->r;
+  const int nct = (r + TB - 1) / TB, nw = (m * r + 1 + TB - 1) / TB;
+  LAUNCH("node_chol", k_node_chol<<<nn, NT, smem_cholinv(r), st>>>(c, list));
+  MRA_FOR_VEC_NJ(h, LAUNCH("node_gt", k_node_gt<V_, J_><<<(unsigned)nn * nw * nct, NT, GS1, st>>>(c, list, nw * nct, nct)));
+}
 
 // assemble_A + node_factor for nodes [rg.begin, rg.begin + rg.count) of level m's list
 int upward_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m, Range rg) {
@@ -335,7 +414,7 @@ int upward_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m, Range r
   const int W = (m + 1) * r + 1, nb = (W - 1 + TB - 1) / TB;
   const int nt = nb * (nb + 1) / 2 + (W + TB - 1) / TB;   // lower tile pairs of the basis block + augmented-row jobs
   MRA_FOR_VEC(h, LAUNCH("assemble_A", k_assemble_A<V_><<<(unsigned)((nn + 15) / 16 * 16) * nt, NT, smem_plain(), st>>>(c, list, nullptr, 0, nn, nt)));
-  MRA_FOR_VEC(h, LAUNCH("node_factor", k_node_factor<V_><<<nn, NT, smem_factor(r), st>>>(c, list)));
+  node_factor(h, st, c, m, list, nn);
   return MRA_OK;
 }
 
@@ -349,10 +428,28 @@ int prior_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m, Range no
   const int r = h->r;
   if (nodes.count <= 0) return MRA_OK;
   const int* list = reinterpret_cast<const int*>(h->ws + L.lists + h->list_off[m]) + nodes.begin;
-  MRA_FOR_VEC(h, LAUNCH("knot_factor", k_knot_factor<V_><<<nodes.count, NT, smem_knot(r), st>>>(c, list)));
+  {
+    const int nt = (r + TB - 1) / TB, npair = nt * (nt + 1) / 2, nkt = (m * r + TB - 1) / TB;
+    MRA_FOR_VEC_NJ(h, LAUNCH("knot_gram", k_knot_gram<V_, J_><<<(unsigned)nodes.count * npair, NT, smem_knot(r), st>>>(c, list, npair)));
+    LAUNCH("knot_chol", k_knot_chol<<<nodes.count, NT, smem_cholinv(r), st>>>(c, list));
+    if (nkt > 0)
+      MRA_FOR_VEC(h, LAUNCH("knot_vkl", k_knot_vkl<V_><<<(unsigned)nodes.count * nt * nkt, NT, GS1, st>>>(c, list, nt * nkt, nkt)));
+  }
   if (tiles.count <= 0) return MRA_OK;
-  const int4* tl = reinterpret_cast<const int4*>(h->ws + L.ptiles + h->ptiles_off[m]) + tiles.begin;
-  MRA_FOR_VEC(h, LAUNCH("prior_tiles", k_prior_tiles<V_><<<tiles.count, NT, smem_prior(r), st>>>(c, tl, m)));
+  // regular tiles run grouped (one chunk stream per <= PG tiles of a node), gathered tiles one CTA each
+  const int nreg = h->n_regular_tiles[m];
+  int t0 = tiles.begin, t1 = tiles.begin + tiles.count;
+  if (h->use_groups && (r & 1) == 0 && t0 < nreg) {
+    const int te = std::min(t1, nreg);
+    const int g0 = h->group_of_tile[m][t0], g1 = h->group_of_tile[m][te - 1] + 1;
+    const int4* gl = reinterpret_cast<const int4*>(h->ws + L.pgroups + h->pgroups_off[m]) + g0;
+    MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", k_prior_groups<J_><<<g1 - g0, NT, smem_pgroups(r), st>>>(c, gl, m)));
+    t0 = te;
+  }
+  if (t0 < t1) {
+    const int4* tl = reinterpret_cast<const int4*>(h->ws + L.ptiles + h->ptiles_off[m]) + t0;
+    MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", k_prior_tiles<V_, J_><<<t1 - t0, NT, smem_prior(r), st>>>(c, tl, m)));
+  }
   return MRA_OK;
 }
 
@@ -365,7 +462,12 @@ int leaf_terms(mra_handle* h, cudaStream_t st, const DevCtx& c, Range rg) {
   const int nbo = (h->max_leaf_obs + TB - 1) / TB;
   const int nt1 = nbo * (nbo + 1) / 2;
   MRA_FOR_VEC(h, LAUNCH("leaf_gram", k_leaf_gram<V_><<<(unsigned)nleaf * nt1, NT, smem_gram(), st>>>(c, leaf_list, 0, nleaf)));
-  MRA_FOR_VEC(h, LAUNCH("leaf_chol", k_leaf_factor<V_><<<nleaf, NT, smem_chol(h->max_leaf_obs), st>>>(c, leaf_list)));
+  for (int p = 0; p < nbo; ++p) {        // left-looking over the 64-wide block columns of S
+    if (p > 0) MRA_FOR_VEC(h, LAUNCH("leaf_upd", k_leaf_upd<V_><<<nleaf, NT, GS1, st>>>(c, leaf_list, p)));
+    LAUNCH("leaf_chol", k_leaf_chol<<<nleaf, NT, smem_cholinv(TB), st>>>(c, leaf_list, p));
+    if (p + 1 < nbo)
+      MRA_FOR_VEC(h, LAUNCH("leaf_trsm", k_leaf_trsm<V_><<<(unsigned)nleaf * (nbo - 1 - p), NT, GS1, st>>>(c, leaf_list, p, nbo - 1 - p)));
+  }
   const int nt3 = std::max(1, (h->max_leaf_W - 1 + TB - 1) / TB);
   MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve_ut<V_><<<(unsigned)nleaf * nt3, NT, smem_solve(), st>>>(c, leaf_list, nt3)));
   return MRA_OK;
@@ -390,6 +492,7 @@ int leaf_predict_terms(mra_handle* h, cudaStream_t st, const DevCtx& c, Range rg
 int reset_pass(mra_handle* h, cudaStream_t st) {
   const Layout& L = h->lay;
   h->launches = 0;
+  h->warnings = 0;
   h->leafq_done = false;
   CU(cudaMemsetAsync(at<double>(h, L.dnode), 0, sizeof(double) * h->n_nodes, st));
   CU(cudaMemsetAsync(at<int>(h, L.status), 0, sizeof(int), st));
@@ -448,7 +551,7 @@ int launch_likelihood_top(mra_handle* h, cudaStream_t st, const double* dev_summ
       const int W = (m + 1) * r + 1;
       dim3 g(nn, std::min(64, (W * W + 255) / 256));
       LAUNCH("assemble_summary", k_assemble_from_summary<<<g, 256, 0, st>>>(c, list, dev_summary, h->slot_base));
-      MRA_FOR_VEC(h, LAUNCH("node_factor", k_node_factor<V_><<<nn, NT, smem_factor(r), st>>>(c, list)));
+      node_factor(h, st, c, m, list, nn);
     }
     for (int mm = std::min(m - 1, (int)h->internal_at.size() - 1); mm >= 0; --mm) {
       int rc = upward_level(h, st, c, mm);
@@ -476,7 +579,7 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
       MRA_FOR_VEC(h, LAUNCH("fold", k_fold<V_><<<(unsigned)h->fold_items.size(), NT, GS1, st>>>(
                                         c, at<int4>(h, L.fold))));
     if (!h->leaf_tiles.empty())
-      MRA_FOR_VEC(h, LAUNCH("predict_fused", k_predict_fused<V_><<<(unsigned)h->leaf_tiles.size(), NT, smem_predict(r), st>>>(
+      MRA_FOR_VEC_NJ(h, LAUNCH("predict_fused", k_predict_fused<V_, J_><<<(unsigned)h->leaf_tiles.size(), NT, smem_predict(r), st>>>(
                                                  c, at<int4>(h, L.ltiles))));
     h->pred_done = true;   // V now holds the posterior-updated basis; results stay cached in mean/var
   }
@@ -488,7 +591,7 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
   }
   if (!h->emit_chunks.empty())
     LAUNCH("unpermute", k_unpermute<<<(unsigned)h->emit_chunks.size(), 256, 0, st>>>(
-                            c.mean, c.var, at<int>(h, L.perm), at<int2>(h, L.chunks), om, os));
+                            c.mean, c.var, at<int>(h, L.perm), at<int2>(h, L.chunks), om, os, h->cov.c0, c.status));
   CU(cudaGetLastError());
   return MRA_OK;
 }
@@ -572,6 +675,28 @@ void build_lists(mra_handle* h) {
   while (!h->internal_at.empty() && h->internal_at.back().empty()) {
     h->internal_at.pop_back();
     h->ptiles_at.pop_back();
+  }
+  // groups of the regular prior tiles: consecutive full tiles of one node, at most PG per group
+  h->pgroups_at.assign(h->ptiles_at.size(), {});
+  h->group_of_tile.assign(h->ptiles_at.size(), {});
+  for (size_t m = 0; m < h->ptiles_at.size(); ++m) {
+    const std::vector<int4>& tl = h->ptiles_at[m];
+    std::vector<int4>& gl = h->pgroups_at[m];
+    std::vector<int>& got = h->group_of_tile[m];
+    const int nreg = h->n_regular_tiles[m];
+    got.resize((size_t)nreg);
+    gl.reserve((size_t)nreg / PG + 16);
+    for (int i = 0; i < nreg; ++i) {
+      const int4& t = tl[i];
+      bool extend = false;
+      if (!gl.empty() && i > 0) {
+        const int4& gb = gl.back();
+        extend = gb.x == t.x && gb.y + gb.z == t.y && gb.z % TB == 0 && gb.z < PG * TB;
+      }
+      if (extend) gl.back().z += t.z;
+      else gl.push_back(make_int4(t.x, t.y, t.z, 0));
+      got[i] = (int)gl.size() - 1;
+    }
   }
   h->leaf_tiles.clear();
   for (int n : h->leaves)
@@ -669,6 +794,7 @@ const char* mra_version(void) { return "pymra_b200 0.1 (sm_100a)"; }
 
 int mra_create(mra_handle** out, int device) {
   if (!out) return MRA_ERR_ARG;
+  const char* env_groups = std::getenv("MRA_PRIOR_GROUPS");
   *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -676,9 +802,14 @@ int mra_create(mra_handle** out, int device) {
   mra_handle* h = new (std::nothrow) mra_handle();
   if (!h) return MRA_ERR_NOMEM;
   h->device = device;
-  if (cudaSetDevice(device) != cudaSuccess) {
-    delete h;
-    return MRA_ERR_CUDA;
+  h->use_groups = !(env_groups && env_groups[0] == '0');      // A/B switch for profiling (default: grouped prior tiles)
+  if (const char* e = std::getenv("MRA_CHOL_MMA")) h->chol_mma = e[0] != '0';
+  {
+    DevGuard g(device);          // validates the ordinal / creates the context; the caller's device is restored
+    if (g.err != cudaSuccess) {
+      delete h;
+      return MRA_ERR_CUDA;
+    }
   }
   *out = h;
   return MRA_OK;
@@ -686,7 +817,7 @@ int mra_create(mra_handle** out, int device) {
 
 int mra_destroy(mra_handle* h) {
   if (h && h->copy_stream) {
-    cudaSetDevice(h->device);
+    DevGuard g(h->device);
     cudaEventDestroy(h->copy_event);
     cudaStreamDestroy(h->copy_stream);
   }
@@ -851,6 +982,13 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       }
     });
   }
+  std::vector<double> my_rows_prior((size_t)nn, 0.0), my_rows_pred((size_t)nn, 0.0);
+  for (size_t m = 0; m < h->ptiles_at.size(); ++m)
+    for (size_t i = 0; i < h->ptiles_at[m].size(); ++i) {
+      const int4& t = h->ptiles_at[m][i];
+      my_rows_prior[t.x] += t.z;
+      if (t.w == 0) my_rows_pred[t.x] += t.z;
+    }
   int64_t leaf_cursor = 0;
   for (int n = 0; n < nn; ++n) {
     NodeDev& d = h->nodes[n];
@@ -878,16 +1016,21 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       linv_off += (long long)r * r;
       d.vk_off = vk_off;
       vk_off += (long long)r * d.level * r;
-      const double nr = (double)d.row_count, rr = (double)r;
+      // rows of this node this rank really works on: all of them unless the node is a replicated top node of a
+      // sharded handle, whose tile list holds only this rank's pieces (+ gathered knot rows, prior pass only)
+      const double nr = my_rows_prior[n], nrp = my_rows_pred[n], rr = (double)r;
       const double Waf = Kv + rr + 1;
-      add_work(h, "knot_factor", rr * rr * Kv + 2.0 * rr * rr * rr / 3.0, 8.0 * (2.0 * rr * Kv + rr * rr));
+      add_work(h, "knot_gram", rr * rr * Kv, 8.0 * (2.0 * rr * Kv + rr * rr / 2));
+      add_work(h, "knot_chol", 2.0 * rr * rr * rr / 3.0, 8.0 * rr * rr);
+      add_work(h, "knot_vkl", 2.0 * rr * rr * Kv, 8.0 * (2.0 * rr * Kv + rr * rr));
       add_work(h, "prior_tiles", 2.0 * nr * rr * Kv + nr * rr * rr, 8.0 * nr * (Kv + rr + 2));
       double fa = 0;     // assemble: symmetric half of W x W, K = n_obs (leaf child) or r (internal child)
       for (int ch = d.child_start; ch < d.child_start + d.child_count; ++ch)
-        if (h->kind[ch] == KIND_INTERNAL) fa += Waf * Waf * rr;
+        if (h->kind[ch] == KIND_INTERNAL && !(h->shard_level > 0 && d.level == h->shard_level - 1)) fa += Waf * Waf * rr;
       add_work(h, "assemble_A", fa, 8.0 * Waf * Waf);
-      add_work(h, "node_factor", 2.0 * rr * rr * rr / 3.0 + (Kv + 1) * rr * rr, 8.0 * (rr * rr + 2 * (Kv + 1) * rr));
-      add_work(h, "predict_fused", nr * rr * rr + 2.0 * nr * rr * Kv + 4.0 * nr * rr, 8.0 * nr * rr);
+      add_work(h, "node_chol", 2.0 * rr * rr * rr / 3.0, 8.0 * 2.0 * rr * rr);
+      add_work(h, "node_gt", (Kv + 1) * rr * rr, 8.0 * (rr * rr + 2 * (Kv + 1) * rr));
+      add_work(h, "predict_fused", nrp * rr * rr + 2.0 * nrp * rr * Kv + 4.0 * nrp * rr, 8.0 * nrp * rr);
     } else {
       if (d.kind == KIND_LEAF) {
         d.obs_off = leaf_obs_off[leaf_cursor];
@@ -915,7 +1058,12 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       if (d.n_obs > 0) h->max_leaf_W = std::max(h->max_leaf_W, d.W);
       const double no = d.n_obs, nl = d.row_count, W = Kv + 1;
       add_work(h, "leaf_gram", no * no * Kv, 8.0 * (no * Kv + no * no / 2));
-      add_work(h, "leaf_chol", no * no * no / 3.0, 8.0 * no * no);
+      for (int pb = 0; pb * TB < d.n_obs; ++pb) {      // blocked factorisation as executed (triangular halves)
+        const double nv = std::min(TB, d.n_obs - pb * TB), Kp = (double)pb * TB, below = no - Kp - nv;
+        add_work(h, "leaf_chol", 2.0 * nv * nv * nv / 3.0, 8.0 * 2.0 * nv * nv);
+        if (pb > 0) add_work(h, "leaf_upd", nv * nv * Kp, 8.0 * (nv * Kp + nv * nv));
+        if (below > 0) add_work(h, "leaf_trsm", below * nv * (2.0 * Kp + nv), 8.0 * (below * (Kp + 2 * nv) + nv * Kp + nv * nv));
+      }
       add_work(h, "leaf_solve", no * no * W, 8.0 * (2 * no * W + no * no / 2));
       add_work(h, "assemble_A", W * W * no, 8.0 * no * W);
       if (d.kind == KIND_LEAF) {
@@ -996,12 +1144,19 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
     h->ptiles_off[m] = po;
     po += (sizeof(int4) * h->ptiles_at[m].size() + 255) & ~size_t(255);
   }
+  h->pgroups_off.assign(h->internal_at.size(), 0);
+  size_t go = 0;
+  for (size_t m = 0; m < h->internal_at.size(); ++m) {
+    h->pgroups_off[m] = go;
+    go += (sizeof(int4) * h->pgroups_at[m].size() + 255) & ~size_t(255);
+  }
   h->leaves_off = lo;
   lo += (sizeof(int) * h->leaves.size() + 255) & ~size_t(255);
   h->sroots_off = lo;
   lo += (sizeof(int) * h->sroots.size() + 255) & ~size_t(255);
   L.lists = ar.take(std::max<size_t>(256, lo));
   L.ptiles = ar.take(std::max<size_t>(256, po));
+  L.pgroups = ar.take(std::max<size_t>(256, go));
   L.gather = ar.take(std::max<size_t>(256, sizeof(int) * h->gather_rows.size()));
   L.chunks = ar.take(std::max<size_t>(256, sizeof(int2) * h->emit_chunks.size()));
   L.ltiles = ar.take(std::max<size_t>(256, sizeof(int4) * h->leaf_tiles.size()));
@@ -1018,7 +1173,7 @@ int mra_bind_workspace(mra_handle* h, void* dev_workspace, size_t bytes) {
   if (!h->planned) return fail(h, MRA_ERR_STATE, "mra_plan must be called first");
   if (bytes < h->lay.total) return fail(h, MRA_ERR_NOMEM, "workspace smaller than mra_plan reported");
   if (reinterpret_cast<uintptr_t>(dev_workspace) % 256) return fail(h, MRA_ERR_ARG, "workspace must be 256-byte aligned");
-  CU(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h);
   h->ws = static_cast<char*>(dev_workspace);
   h->ws_bytes = bytes;
   int rc = configure_kernels(h);
@@ -1035,7 +1190,7 @@ static int upload_impl(mra_handle* h, const double* locs, const double* obs, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const Layout& L = h->lay;
   const size_t N = (size_t)h->N;
-  CU(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h);
   CU(cudaMemcpyAsync(h->ws + L.nodes, h->nodes.data(), sizeof(NodeDev) * h->nodes.size(), cudaMemcpyHostToDevice, st));
   if (!h->knot_rows.empty())
     CU(cudaMemcpyAsync(h->ws + L.knot_rows, h->knot_rows.data(), sizeof(int) * h->knot_rows.size(), cudaMemcpyHostToDevice, st));
@@ -1052,6 +1207,9 @@ static int upload_impl(mra_handle* h, const double* locs, const double* obs, con
     if (!h->ptiles_at[m].empty())
       CU(cudaMemcpyAsync(h->ws + L.ptiles + h->ptiles_off[m], h->ptiles_at[m].data(),
                          sizeof(int4) * h->ptiles_at[m].size(), cudaMemcpyHostToDevice, st));
+    if (!h->pgroups_at[m].empty())
+      CU(cudaMemcpyAsync(h->ws + L.pgroups + h->pgroups_off[m], h->pgroups_at[m].data(),
+                         sizeof(int4) * h->pgroups_at[m].size(), cudaMemcpyHostToDevice, st));
   }
   if (!h->sroots.empty())
     CU(cudaMemcpyAsync(h->ws + L.lists + h->sroots_off, h->sroots.data(), sizeof(int) * h->sroots.size(),
@@ -1124,7 +1282,6 @@ int mra_set_nugget(mra_handle* h, double R) {
 static int ready_to_run(mra_handle* h) {
   if (!h->uploaded) return fail(h, MRA_ERR_STATE, "mra_upload_data must be called first");
   if (!h->cov_set || !h->R_set) return fail(h, MRA_ERR_STATE, "mra_set_cov and mra_set_nugget must be called first");
-  CU(cudaSetDevice(h->device));
   return MRA_OK;
 }
 
@@ -1132,6 +1289,7 @@ int mra_run_likelihood_async(mra_handle* h, void* stream) {
   if (!h) return MRA_ERR_ARG;
   if (h->shard_level > 0)
     return fail(h, MRA_ERR_STATE, "sharded handle: use mra_run_likelihood_local_async / _top_async");
+  DEVICE_SCOPE(h);
   int rc = ready_to_run(h);
   if (rc) return rc;
   rc = launch_likelihood_local(h, static_cast<cudaStream_t>(stream), nullptr);
@@ -1174,6 +1332,7 @@ int mra_summary_size(const mra_handle* h, int64_t* n_doubles) {
 int mra_run_likelihood_local_async(mra_handle* h, void* stream, double* dev_summary) {
   if (!h) return MRA_ERR_ARG;
   if (h->shard_level > 0 && !dev_summary) return fail(h, MRA_ERR_ARG, "sharded handle needs a summary buffer");
+  DEVICE_SCOPE(h);
   int rc = ready_to_run(h);
   if (rc) return rc;
   return launch_likelihood_local(h, static_cast<cudaStream_t>(stream), dev_summary);
@@ -1182,6 +1341,7 @@ int mra_run_likelihood_local_async(mra_handle* h, void* stream, double* dev_summ
 int mra_run_likelihood_top_async(mra_handle* h, void* stream, const double* dev_summary) {
   if (!h) return MRA_ERR_ARG;
   if (h->shard_level > 0 && !dev_summary) return fail(h, MRA_ERR_ARG, "sharded handle needs a summary buffer");
+  DEVICE_SCOPE(h);
   int rc = ready_to_run(h);
   if (rc) return rc;
   return launch_likelihood_top(h, static_cast<cudaStream_t>(stream), dev_summary);
@@ -1229,6 +1389,7 @@ int mra_stream_begin_async(mra_handle* h, void* stream, const int64_t* knot_rows
   if (!h) return MRA_ERR_ARG;
   if (h->shard_level > 2 || h->n_parts <= 0)
     return fail(h, MRA_ERR_STATE, "streamed evaluation needs an internal root and a handle that is unsharded or sharded at level 1 or 2");
+  DEVICE_SCOPE(h);
   int rc = ready_to_run(h);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1253,14 +1414,14 @@ int mra_stream_part_async(mra_handle* h, void* stream, int32_t part, const int64
   if (h->stream_parts_done & (1 << part)) return fail(h, MRA_ERR_STATE, "part already evaluated");
   if (!(h->my_parts & (1 << part))) return fail(h, MRA_ERR_ARG, "this part belongs to another rank");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h);
   DevCtx c = make_ctx(h);
   int rc = upload_knot_ranges(h, st, knot_rows, h->part_knots[part], h->part_gather[part]);
   if (rc) return rc;
   const int nl = (int)h->internal_at.size();
   if (h->part_gtiles[part].count > 0) {     // sharded at level 2: the root's basis at the knots of the part's level-1 node
     const int4* tl = reinterpret_cast<const int4*>(h->ws + h->lay.ptiles + h->ptiles_off[0]) + h->part_gtiles[part].begin;
-    MRA_FOR_VEC(h, LAUNCH("prior_tiles", k_prior_tiles<V_><<<h->part_gtiles[part].count, NT, smem_prior(h->r), st>>>(c, tl, 0)));
+    MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", k_prior_tiles<V_, J_><<<h->part_gtiles[part].count, NT, smem_prior(h->r), st>>>(c, tl, 0)));
   }
   for (int m = 1; m < nl; ++m) {
     rc = prior_level(h, st, c, m, h->part_nodes[m][part], h->part_tiles[m][part]);
@@ -1289,7 +1450,7 @@ int mra_stream_end_async(mra_handle* h, void* stream) {
   if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
   if (h->stream_parts_done != h->my_parts) return fail(h, MRA_ERR_STATE, "not every part has been evaluated");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h);
   DevCtx c = make_ctx(h);
   int rc = upward_level(h, st, c, 0);
   if (rc) return rc;
@@ -1305,7 +1466,7 @@ int mra_stream_sync_knots(mra_handle* h, void* stream, const int64_t* knot_rows)
   if (!h || !knot_rows) return MRA_ERR_ARG;
   if (!h->uploaded) return fail(h, MRA_ERR_STATE, "mra_upload_data must be called first");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h);
   if (h->knot_rows.empty()) return MRA_OK;
   int rc = upload_knot_ranges(h, st, knot_rows, std::vector<Range>{Range{0, (int)h->knot_rows.size()}});
   if (rc) return rc;
@@ -1324,7 +1485,7 @@ int mra_stream_end_local_async(mra_handle* h, void* stream, double* dev_summary)
   if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
   if (h->stream_parts_done != h->my_parts) return fail(h, MRA_ERR_STATE, "not every part of this rank has been evaluated");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h);
   DevCtx c = make_ctx(h);
   int rc = export_summaries(h, st, c, dev_summary);
   if (rc) return rc;
@@ -1337,6 +1498,7 @@ int mra_stream_end_local_async(mra_handle* h, void* stream, double* dev_summary)
 int mra_fetch_likelihood(mra_handle* h, void* stream, double out[2]) {
   if (!h || !out) return MRA_ERR_ARG;
   if (!h->lik_done) return fail(h, MRA_ERR_STATE, "no likelihood pass has been run");
+  DEVICE_SCOPE(h);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CU(cudaMemcpyAsync(out, h->ws + h->lay.out, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   return check_status(h, st);
@@ -1352,18 +1514,25 @@ int mra_run_predict_dev(mra_handle* h, void* stream, double* dev_mean, double* d
   if (!h) return MRA_ERR_ARG;
   if (!h->lik_done) return fail(h, MRA_ERR_STATE, "mra_run_likelihood must be called first");
   if (!h->want_predict) return fail(h, MRA_ERR_STATE, "mra_plan was called with want_predict = 0");
-  CU(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h);
   return launch_predict(h, static_cast<cudaStream_t>(stream), dev_mean, dev_sd);
 }
 
 int mra_run_predict(mra_handle* h, void* stream, double* mean, double* sd) {
   if (!h || !mean || !sd) return MRA_ERR_ARG;
+  DEVICE_SCOPE(h);
   int rc = mra_run_predict_dev(h, stream, nullptr, nullptr);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CU(cudaMemcpyAsync(mean, h->ws + h->lay.out_mean, sizeof(double) * h->N, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(sd, h->ws + h->lay.out_sd, sizeof(double) * h->N, cudaMemcpyDeviceToHost, st));
   return check_status(h, st);
+}
+
+int mra_last_warnings(const mra_handle* h, int32_t* flags) {
+  if (!h || !flags) return MRA_ERR_ARG;
+  *flags = h->warnings;
+  return MRA_OK;
 }
 
 int mra_last_launches(const mra_handle* h, int64_t* n) {
@@ -1394,7 +1563,7 @@ int mra_profile_enable(mra_handle* h, int on) {
 
 int mra_profile_read(mra_handle* h, char* buf, size_t buflen) {
   if (!h || !buf || buflen == 0) return MRA_ERR_ARG;
-  CU(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h);
   CU(cudaDeviceSynchronize());
   for (auto& r : h->prof_recs) {
     float ms = 0.f;
@@ -1453,7 +1622,8 @@ int64_t mra_debug_fetch(mra_handle* h, const char* what, int node, double* out, 
     if (d.kind != KIND_INTERNAL && !(w == "S" || w == "UT" || w == "QT")) return fail(h, MRA_ERR_ARG, "internal buffer of a leaf");
   }
   cnt = std::min(cnt, max_doubles);
-  if (cudaSetDevice(h->device) != cudaSuccess) return MRA_ERR_CUDA;
+  DevGuard dev_guard_(h->device);
+  if (dev_guard_.err != cudaSuccess) return MRA_ERR_CUDA;
   if (cudaDeviceSynchronize() != cudaSuccess) return fail(h, MRA_ERR_CUDA, "device synchronize failed");
   if (cudaMemcpy(out, h->ws + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost) != cudaSuccess)
     return fail(h, MRA_ERR_CUDA, "debug copy failed");

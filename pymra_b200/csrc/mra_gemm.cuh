@@ -52,24 +52,31 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 }
 
 // Element (i, j, e) of a thread: tile row 16*warp + 8*i + (lane >> 2), column 8*j + 2*(lane & 3) + e.
-struct Acc {
-  double v[2][8][2];
+// NJ = number of 8-column groups of the tile: 8 for the square 64 x 64 tile; kernels whose output is only r <= 48
+// columns wide (r0 = 16 / 32: BASELINE cfg4 / cfg3) use 64 x 16 / 64 x 32 / 64 x 48 tiles (NJ = 2 / 4 / 6) so that no
+// DMMA, fragment load or B-operand copy is spent on zero padding.
+template <int NJ>
+struct AccT {
+  static constexpr int kNJ = NJ;
+  double v[2][NJ][2];
   __device__ __forceinline__ void zero() {
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j][0] = v[i][j][1] = 0.0;
+      for (int j = 0; j < NJ; ++j) v[i][j][0] = v[i][j][1] = 0.0;
   }
   __device__ __forceinline__ void negate() {
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         v[i][j][0] = -v[i][j][0];
         v[i][j][1] = -v[i][j][1];
       }
   }
 };
+using Acc = AccT<8>;
+constexpr int nj_for(int r) { return r <= 16 ? 2 : r <= 32 ? 4 : r <= 48 ? 6 : 8; }
 
 __device__ __forceinline__ void cp_async_16(double* smem, const double* gmem, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -92,7 +99,7 @@ __device__ __forceinline__ int stage_pos(int row, int k) {
 
 // Issue the copies of one chunk (k0 .. k0+KC) of one operand.  `dummy` is any valid global address
 // (used with src-size 0, which reads nothing and zero-fills).
-template <int VEC>
+template <int VEC, int NROWS = TB>
 __device__ __forceinline__ void stage_load(double* st, const double* const* rows, int k0, int K,
                                            const double* dummy) {
   if (VEC == 2) {
@@ -100,7 +107,7 @@ __device__ __forceinline__ void stage_load(double* st, const double* const* rows
     const int k = k0 + kc;
     const int nv = min(max(K - k, 0), 2) * 8;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < (NROWS + 15) / 16; ++i) {
       const int row = rb + 16 * i;
       const double* p = rows[row];
       cp_async_16(st + stage_pos(row, kc), p ? p + k : dummy, p ? nv : 0);
@@ -110,7 +117,7 @@ __device__ __forceinline__ void stage_load(double* st, const double* const* rows
     const int k = k0 + kc;
     const int nv = (k < K) ? 8 : 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < (NROWS + 7) / 8; ++i) {
       const int row = rb + 8 * i;
       const double* p = rows[row];
       cp_async_8(st + stage_pos(row, kc), p ? p + k : dummy, p ? nv : 0);
@@ -122,8 +129,8 @@ __device__ __forceinline__ void stage_load(double* st, const double* const* rows
 // k index kk (0..15) inside the chunk.
 // mrows: valid rows of the output tile; warps whose 16 rows lie outside are skipped (their accumulators
 // keep their value, zero if the tile was zeroed).  Column-group predication was measured slower (r01g).
-template <class GA, class GB>
-__device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb, int mrows = TB, int ncols = TB) {
+template <int NJ, class GA, class GB>
+__device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows = TB, int ncols = TB) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp * 16;
   if (wm >= mrows) return;
@@ -131,15 +138,15 @@ __device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb, int mrows = TB
   const int g = lane >> 2, q = lane & 3;
 #pragma unroll
   for (int ks = 0; ks < KC; ks += 4) {
-    double a[2], b[8];
+    double a[2], b[NJ];
 #pragma unroll
     for (int i = 0; i < 2; ++i) a[i] = ga(wm + i * 8 + g, ks + q);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = gb(j * 8 + g, ks + q);
+    for (int j = 0; j < NJ; ++j) b[j] = gb(j * 8 + g, ks + q);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dmma884(acc.v[i][j], a[i], b[j]);
+      for (int j = 0; j < NJ; ++j) dmma884(acc.v[i][j], a[i], b[j]);
   }
 }
 
@@ -147,9 +154,10 @@ __device__ __forceinline__ void chunk_mma(Acc& acc, GA ga, GB gb, int mrows = TB
 //   A_GLOBAL: fa(rr) -> const double* row pointer (nullptr = zero row); else fa(rr, k) -> element
 //   (shared-memory resident operand; must return 0 for k >= K).  Same for B.
 // Must be called by all 128 threads; safe to call back to back (leading barrier).
-template <int VEC, bool A_GLOBAL, bool B_GLOBAL, class FA, class FB, class SM>
-__device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, SM& sm, const double* dummy,
+template <int VEC, bool A_GLOBAL, bool B_GLOBAL, int NJ, class FA, class FB, class SM>
+__device__ __forceinline__ void tile_gemm(AccT<NJ>& acc, int K, FA fa, FB fb, SM& sm, const double* dummy,
                                           int mrows = TB, int ncols = TB) {
+  constexpr int BR = 8 * NJ;     // rows of the B operand (= columns of the tile) that exist
   __syncthreads();   // previous users of the stages / row tables (and of resident operands) are done
   if (A_GLOBAL) {
     if (threadIdx.x < TB) {
@@ -158,7 +166,10 @@ __device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, SM& sm,
   }
   if (B_GLOBAL) {
     if (threadIdx.x >= NT - TB) {
-      if constexpr (B_GLOBAL) sm.row_b[0][threadIdx.x - (NT - TB)] = fb((int)threadIdx.x - (NT - TB));
+      if constexpr (B_GLOBAL) {
+        const int rr = (int)threadIdx.x - (NT - TB);
+        sm.row_b[0][rr] = rr < BR ? fb(rr) : nullptr;
+      }
     }
   }
   __syncthreads();
@@ -167,7 +178,7 @@ __device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, SM& sm,
   for (int s = 0; s < NSTAGE - 1; ++s) {
     if (s < nk) {
       if (A_GLOBAL) stage_load<VEC>(sm.a[s], sm.row_a[0], s * KC, K, dummy);
-      if (B_GLOBAL) stage_load<VEC>(sm.b[s], sm.row_b[0], s * KC, K, dummy);
+      if (B_GLOBAL) stage_load<VEC, BR>(sm.b[s], sm.row_b[0], s * KC, K, dummy);
     }
     cp_async_commit();
   }
@@ -181,7 +192,7 @@ __device__ __forceinline__ void tile_gemm(Acc& acc, int K, FA fa, FB fb, SM& sm,
       if (nb >= NSTAGE) nb -= NSTAGE;
       if (kn < nk) {
         if (A_GLOBAL) stage_load<VEC>(sm.a[nb], sm.row_a[0], kn * KC, K, dummy);
-        if (B_GLOBAL) stage_load<VEC>(sm.b[nb], sm.row_b[0], kn * KC, K, dummy);
+        if (B_GLOBAL) stage_load<VEC, BR>(sm.b[nb], sm.row_b[0], kn * KC, K, dummy);
       }
       cp_async_commit();
     }
@@ -211,15 +222,18 @@ struct NoGen {
   __device__ double operator()(int, int) const { return 0.0; }
 };
 
-template <int VEC, bool GEN = false, bool CACHE_PTRS = true, class FA, class FB, class FK, class SM, class FG = NoGen>
-__device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, FK fk, SM& sm,
+template <int VEC, bool GEN = false, bool CACHE_PTRS = true, int NJ, class FA, class FB, class FK, class SM, class FG = NoGen>
+__device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB fb, FK fk, SM& sm,
                                               const double* dummy, int mrows = TB, int ncols = TB, FG fg = FG()) {
+  constexpr int BR = 8 * NJ;            // rows of the B operand that exist
+  constexpr int BI = (BR + 15) / 16;    // 16-row groups of B a thread copies (16-byte path)
   __syncthreads();
   for (int s = 0; s < nseg; ++s) {
     if (threadIdx.x < TB) {
       if (!(GEN && s == nseg - 1)) sm.row_a[s][threadIdx.x] = fa(s, (int)threadIdx.x);
     } else {
-      sm.row_b[s][threadIdx.x - TB] = fb(s, (int)threadIdx.x - TB);
+      const int rr = (int)threadIdx.x - TB;
+      sm.row_b[s][rr] = rr < BR ? fb(s, rr) : nullptr;
     }
     if (threadIdx.x == 0) sm.seg_k[s] = fk(s);
   }
@@ -246,7 +260,7 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (!gen) pa[i] = sm.row_a[lseg][rb + 16 * i];
-            pb[i] = sm.row_b[lseg][rb + 16 * i];
+            if (i < BI) pb[i] = sm.row_b[lseg][rb + 16 * i];
           }
         }
         const int k = lk0 + kc;
@@ -263,7 +277,7 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
           } else {
             cp_async_16(sm.a[buf] + pos, pa[i] ? pa[i] + k : dummy, pa[i] ? nv : 0);
           }
-          cp_async_16(sm.b[buf] + pos, pb[i] ? pb[i] + k : dummy, pb[i] ? nv : 0);
+          if (i < BI) cp_async_16(sm.b[buf] + pos, pb[i] ? pb[i] + k : dummy, pb[i] ? nv : 0);
         }
       } else {
         if (gen) {
@@ -277,7 +291,7 @@ __device__ __forceinline__ void tile_gemm_seg(Acc& acc, int nseg, FA fa, FB fb, 
         } else {
           stage_load<VEC>(sm.a[buf], sm.row_a[lseg], lk0, K, dummy);
         }
-        stage_load<VEC>(sm.b[buf], sm.row_b[lseg], lk0, K, dummy);
+        stage_load<VEC, BR>(sm.b[buf], sm.row_b[lseg], lk0, K, dummy);
       }
       lk0 += KC;
     }
@@ -312,8 +326,8 @@ __device__ __forceinline__ int kstage_pos(int kr, int n) { return kr * TB + (n ^
 // acc += A * B with A K-contiguous rows in global memory (fa(rr) -> row pointer) and B K-major in global
 // memory: B[k][n] = bbase[k * ldb + n], k < K, n < ncols (zero outside).  Used where the contraction index
 // is the row index of a stored block (left-multiplication of a block by a small matrix).
-template <int VEC, class FA, class SM>
-__device__ __forceinline__ void tile_gemm_kmajorB(Acc& acc, int K, FA fa, const double* bbase, long long ldb,
+template <int VEC, int NJ, class FA, class SM>
+__device__ __forceinline__ void tile_gemm_kmajorB(AccT<NJ>& acc, int K, FA fa, const double* bbase, long long ldb,
                                                   int ncols, SM& sm, const double* dummy) {
   __syncthreads();
   if (threadIdx.x < TB) sm.row_a[0][threadIdx.x] = fa((int)threadIdx.x);
@@ -372,9 +386,10 @@ __device__ __forceinline__ void tile_gemm_kmajorB(Acc& acc, int K, FA fa, const 
 // out += Areg * B^T where Areg is a 64 x 64 tile held in accumulator layout (columns >= K must be zero
 // or K a multiple of 4 covering them) and K <= 64.  B_GLOBAL: fb(rr) -> row pointer, streamed through the
 // cp.async stages; else fb(rr, k) -> element of a shared-memory resident operand.
-template <int VEC, bool B_GLOBAL, class FB, class SM>
-__device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB fb, SM& sm,
+template <int VEC, bool B_GLOBAL, int NJ, int NJA, class FB, class SM>
+__device__ __forceinline__ void tile_gemm_regA(AccT<NJ>& out, const AccT<NJA>& A, int K, FB fb, SM& sm,
                                                const double* dummy, int mrows = TB, int ncols = TB) {
+  constexpr int BR = 8 * NJ;
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const bool active = (int)(threadIdx.x >> 5) * 16 < mrows;
@@ -382,26 +397,26 @@ __device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB
   __syncthreads();
   if (B_GLOBAL) {
     if (threadIdx.x < TB) {
-      if constexpr (B_GLOBAL) sm.row_b[0][threadIdx.x] = fb((int)threadIdx.x);
+      if constexpr (B_GLOBAL) sm.row_b[0][threadIdx.x] = (int)threadIdx.x < BR ? fb((int)threadIdx.x) : nullptr;
     }
     __syncthreads();
   }
-  const int nk = (K + KC - 1) / KC;      // <= 4
+  const int nk = (K + KC - 1) / KC;      // <= NJA / 2
   if (B_GLOBAL) {
 #pragma unroll
     for (int s = 0; s < NSTAGE - 1; ++s) {
-      if (s < nk) stage_load<VEC>(sm.b[s], sm.row_b[0], s * KC, K, dummy);
+      if (s < nk) stage_load<VEC, BR>(sm.b[s], sm.row_b[0], s * KC, K, dummy);
       cp_async_commit();
     }
   }
 #pragma unroll
-  for (int kt = 0; kt < TB / KC; ++kt) {
+  for (int kt = 0; kt < (8 * NJA + KC - 1) / KC; ++kt) {
     if (kt < nk) {
       const int buf = kt % NSTAGE;
       if (B_GLOBAL) {
         cp_async_wait<NSTAGE - 2>();
         __syncthreads();
-        if (kt + NSTAGE - 1 < nk) stage_load<VEC>(sm.b[(kt + NSTAGE - 1) % NSTAGE], sm.row_b[0], (kt + NSTAGE - 1) * KC, K, dummy);
+        if (kt + NSTAGE - 1 < nk) stage_load<VEC, BR>(sm.b[(kt + NSTAGE - 1) % NSTAGE], sm.row_b[0], (kt + NSTAGE - 1) * KC, K, dummy);
         cp_async_commit();
       }
       const double* sb = sm.b[buf];
@@ -410,22 +425,23 @@ __device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB
       for (int ks = 0; ks < KC; ks += 4) {
         const int st = (kt * KC + ks) >> 2;            // k-step index 0..15 -> source tile st>>1, half st&1
         const int src = (lane & ~3) | (((st & 1) << 1) | (q >> 1));
-        double a[2], b[8];
+        if ((st >> 1) >= NJA) continue;                // beyond the columns A holds (NJA odd)
+        double a[2], b[NJ];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const double v0 = __shfl_sync(0xffffffffu, A.v[i][st >> 1][0], src);
-          const double v1 = __shfl_sync(0xffffffffu, A.v[i][st >> 1][1], src);
+          const double v0 = __shfl_sync(0xffffffffu, A.v[i][(st >> 1) < NJA ? (st >> 1) : 0][0], src);
+          const double v1 = __shfl_sync(0xffffffffu, A.v[i][(st >> 1) < NJA ? (st >> 1) : 0][1], src);
           a[i] = (q & 1) ? v1 : v0;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           if constexpr (B_GLOBAL) b[j] = sb[stage_pos(j * 8 + g, ks + q)];
           else b[j] = fb(j * 8 + g, kt * KC + ks + q);
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dmma884(out.v[i][j], a[i], b[j]);
+          for (int j = 0; j < NJ; ++j) dmma884(out.v[i][j], a[i], b[j]);
       }
     }
   }
@@ -433,29 +449,29 @@ __device__ __forceinline__ void tile_gemm_regA(Acc& out, const Acc& A, int K, FB
 }
 
 // acc.v = f(row, col, acc.v) element-wise (transform in registers).
-template <class F>
-__device__ __forceinline__ void tile_transform(Acc& acc, F f) {
+template <int NJ, class F>
+__device__ __forceinline__ void tile_transform(AccT<NJ>& acc, F f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp * 16;
   const int g = lane >> 2, q = lane & 3;
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < NJ; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) acc.v[i][j][e] = f(wm + i * 8 + g, j * 8 + q * 2 + e, acc.v[i][j][e]);
 }
 
 // f(row, col, value) for every accumulator element owned by this thread.
-template <class F>
-__device__ __forceinline__ void tile_epilogue(const Acc& acc, F f) {
+template <int NJ, class F>
+__device__ __forceinline__ void tile_epilogue(const AccT<NJ>& acc, F f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp * 16;
   const int g = lane >> 2, q = lane & 3;
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < NJ; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) f(wm + i * 8 + g, j * 8 + q * 2 + e, acc.v[i][j][e]);
 }

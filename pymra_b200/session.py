@@ -42,6 +42,7 @@ class DeviceSession(object):
         self._set_structure()
         self.timings["set_structure"] = time.perf_counter() - t0
         self.group, self.world, self.rank, self.shard_level, self.summary = None, 1, 0, 0, None
+        self._collective = False    # True when the ranks of a real process group run this session together
         self.gather = gather        # sharded predict(): "all" = every rank gets all N results, "root" = rank 0 only
         if group is not None or emulate is not None:
             from .shard import plan_shards
@@ -51,6 +52,7 @@ class DeviceSession(object):
                 import torch.distributed as dist
                 self.group = None if group is True else group
                 self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+                self._collective = True
             s, role, _ = plan_shards(structure, self.world, self.rank)
             if s:
                 role = np.ascontiguousarray(role, dtype=np.int8)
@@ -185,7 +187,17 @@ class DeviceSession(object):
 
     def fetch_likelihood(self):
         out = (C.c_double * 2)()
-        self.check(self.lib.mra_fetch_likelihood(self.h, self.stream(), out))
+        st = self.lib.mra_fetch_likelihood(self.h, self.stream(), out)
+        if self.shard_level and self._collective:
+            # a failure on one rank only (a non-positive pivot in one shard) must not leave the others running
+            # into the next collective on their own: every rank learns about it here and raises together
+            import torch
+            import torch.distributed as dist
+            flag = torch.tensor([1 if st != 0 else 0], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            if int(flag.item()) and st == 0:
+                raise _ffi.MraError(-4, "another rank of the group failed its pass (its own exception has the cause)")
+        self.check(st)
         return float(out[0]), float(out[1])
 
     def predict(self):
@@ -229,6 +241,12 @@ class DeviceSession(object):
             dist.all_reduce(sd_t, group=self.group)
 
     # ---- counters
+    def warnings(self):
+        """MRA_WARN_* bits the passes have raised since the last likelihood pass started (include/pymra_b200.h)."""
+        f = C.c_int32()
+        self.check(self.lib.mra_last_warnings(self.h, C.byref(f)))
+        return int(f.value)
+
     def launches(self):
         n = C.c_int64()
         self.check(self.lib.mra_last_launches(self.h, C.byref(n)))

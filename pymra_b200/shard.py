@@ -76,7 +76,7 @@ _I32_FIELDS = ("node_level", "node_parent", "node_kind", "node_child_start", "no
                "node_row_start", "node_row_count", "node_knot_off")
 
 
-def build_structure_group(locs, r, M, J, critDepth, group=None, async_start=None):
+def build_structure_group(locs, r, M, J, critDepth, group=None, async_start=None, device=None):
     """The tree for a process group.  The reference's knot draws are one sequential legacy-RNG stream
     (pyMRA/MRANode.py:191-193 in DFS pre-order), so N ranks building redundantly only fight for the host's
     memory bandwidth.  Instead group rank 0 runs the native builder with all the host threads and broadcasts
@@ -94,7 +94,9 @@ def build_structure_group(locs, r, M, J, critDepth, group=None, async_start=None
     rank = dist.get_rank(group)
     src = dist.get_global_rank(group, 0) if group is not None else 0
     on_gpu = dist.get_backend(group) == "nccl"
-    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    # communication buffers live on the device the session will use (MRATree's `device`), not on whatever the
+    # process' current device happens to be
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device) if on_gpu else torch.device("cpu")
     locs = np.ascontiguousarray(locs, dtype=np.float64)
     N = len(locs)
     header = torch.zeros(8, dtype=torch.int64)
@@ -190,7 +192,7 @@ class GroupStreamBuild(object):
     state.  Broadcasts run on their own high-priority stream so that they never queue behind the evaluation
     kernels of a rank that is still busy with an earlier subtree."""
 
-    def __init__(self, locs, r, M, J, critDepth, group=None):
+    def __init__(self, locs, r, M, J, critDepth, group=None, device=None):
         import torch
         import torch.distributed as dist
 
@@ -199,7 +201,8 @@ class GroupStreamBuild(object):
         self.rank = dist.get_rank(group)
         self.src = dist.get_global_rank(group, 0) if group is not None else 0
         self.on_gpu = dist.get_backend(group) == "nccl"
-        self.dev = torch.device("cuda", torch.cuda.current_device()) if self.on_gpu else torch.device("cpu")
+        self.dev = (torch.device("cuda", torch.cuda.current_device() if device is None else device)
+                    if self.on_gpu else torch.device("cpu"))
         # one side stream per device for the whole process: the caching allocator keeps a pool per stream, so a
         # fresh stream per construction would mean fresh cudaMallocs (slow, and synchronising, once NCCL has
         # enabled peer access) for every forwarded payload

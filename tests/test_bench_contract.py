@@ -31,8 +31,25 @@ def test_reference_arm_prints_one_contract_line():
     modes = cb["modes"]
     assert modes["serial"]["evals_per_s"] > 0
     assert modes["serial"]["blas_threads"] >= 1
-    assert "error" not in modes["multiprocess"] and modes["multiprocess"]["processes"] >= 1
-    assert d["value"] == max(modes["serial"]["evals_per_s"], modes["multiprocess"]["evals_per_s"])
+    assert "error" not in modes["fork_critDepth0"] and modes["fork_critDepth0"]["processes"] == 4     # real forks
+    assert "error" not in modes["side_by_side"] and modes["side_by_side"]["processes"] >= 1
+    assert d["value"] == max(m["evals_per_s"] for m in modes.values())
+    # the line says what it is: an extrapolated estimate from a smaller sample, with consistent per-step time
+    assert d["same_config"] is False and d["extrapolated"] is True and d["sample_grid"] == [60, 60]
+    assert abs(d["ms_per_step"] - 1e3 / d["value"]) < 1e-6 * d["ms_per_step"]
+
+
+def test_bench_and_parity_inputs_are_the_same_field():
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    from _util import FULLSIZE_CASES, fullsize_inputs
+    a = bench.make_inputs(40, 0.4)
+    b = fullsize_inputs(40, 0.4)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1], equal_nan=True)
+    for k in ("cfg3", "cfg4", "cfg5"):
+        assert bench.WORKLOADS[k] == FULLSIZE_CASES[k]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -1,37 +1,56 @@
-"""Parity of the CUDA path (through the C ABI, via pymra_b200.MRATree) against the golden vectors
-recorded from the unmodified reference and against the oracle on the same seeded inputs.
+"""Parity of the CUDA path (through the C ABI, via pymra_b200.MRATree).
 
-Tolerances: north_star asks 1e-9 relative (likelihood / predictions / sd).  Where the reference's own
-FP64 noise is above that (ill-conditioned fixtures) the bound is a multiple of the
-measured oracle-vs-reference gap, i.e. "within the reference's own noise floor".
+Three references, in decreasing authority:
+  * TRUTH  -- the exact dense posterior under the MRA-implied covariance in extended precision
+              (oracle/dense_truth.c; committed per fixture under tests/golden/truth/, computed on the fly for the
+              seeded cases).  north_star's 1e-9 is asserted against it.
+  * the golden vectors recorded from the unmodified reference (tests/golden/), and
+  * the oracle port (oracle/mra_oracle.py) on the same seeded inputs.
+The reference's own FP64 result is not exact: it inverts ill-conditioned knot covariances with LU.
+Where ITS distance to the truth is above 1e-9, the CUDA path must be at least as close to the truth as the
+reference is (no slack factor); everywhere else it must be within 1e-9.  tools/parity_table.py prints the achieved
+errors (profiles/r04_parity_table.md).
 """
 import numpy as np
 import pytest
 
-from _util import errs, golden_names, load_golden, oracle_for, tree_for
+from _util import (FULLSIZE_CASES, errs, fullsize_parity, golden_names, load_golden, load_truth, oracle_for,
+                   seeded_case, tree_for)
 
 pytestmark = pytest.mark.gpu
 
-LIK_TOL, MEAN_TOL, SD_TOL = 1e-9, 1e-9, 1e-9
+TOL = 1e-9          # likelihood relative, mean absolute (unit-scale fields), sd relative
+
+
+def assert_close_to_truth(got, ref_errs, truth, what):
+    """got = (lik, mean, sd) of the CUDA path; ref_errs = errors of the reference (or the port) against the truth."""
+    e = errs(got[0], got[1], got[2], truth)
+    scale = max(1.0, float(np.max(np.abs(truth["mean"]))))
+    for name, mine, theirs, tol in zip(("lik", "mean", "sd"), e, ref_errs, (TOL, TOL * scale, TOL)):
+        assert mine <= max(tol, theirs), (what, name, "cuda", mine, "reference", theirs)
+    return e
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_cuda_matches_reference_and_oracle(name):
+def test_cuda_vs_truth_and_reference(name):
     g = load_golden(name)
-    o = oracle_for(g)
-    fl, fm, fs = errs(o["lik"], o["mean"], o["sd"], g)          # reference's own noise floor
+    T = load_truth(name)
     t = tree_for(g)
     assert t.M == int(g["M_eff"]) and t.J == int(g["J_eff"])
     lik = float(t.getLikelihood())
     mean, sd = t.predict()
     assert mean.shape == (len(g["locs"]), 1) and isinstance(mean, np.matrix) and sd.shape == (len(g["locs"]),)
-    scale = max(1.0, float(np.max(np.abs(g["mean"]))))
-    for ref in (g, o):
-        rl, em, es = errs(lik, mean, sd, ref)
-        assert rl <= max(LIK_TOL, 20 * fl), ("lik", rl, fl)
-        assert em <= max(MEAN_TOL * scale, 20 * fm), ("mean", em, fm)
-        assert es <= max(SD_TOL, 20 * fs), ("sd", es, fs)
     assert np.array_equal(t.root.kInds, g["root_kinds"])
+    ref = errs(float(g["lik"]), g["mean"], g["sd"], T)           # how far the unmodified reference is from the truth
+    assert_close_to_truth((lik, mean, sd), ref, T, name)
+    # and the three implementations agree with each other to the reference's own accuracy
+    o = oracle_for(g)
+    floor = [max(a, b) for a, b in zip(ref, errs(o["lik"], o["mean"], o["sd"], T))]
+    scale = max(1.0, float(np.max(np.abs(g["mean"]))))
+    for other in (g, o):
+        rl, em, es = errs(lik, mean, sd, other)
+        assert rl <= max(TOL, 2 * floor[0]) and em <= max(TOL * scale, 2 * floor[1]) and es <= max(TOL, 2 * floor[2]), \
+            (name, rl, em, es, floor)
 
 
 def test_refit_equals_fresh_construction():
@@ -62,38 +81,62 @@ def test_errors_cross_the_abi_as_exceptions():
         MRATree(g["locs"], 8, lambda a, b: mt.ExpCovFun(a, b, l=0.3), g["obs"].ravel(), 1e-2)
 
 
-@pytest.mark.parametrize("n,M,r,family,frac", [(64, 1, 80, "exp", 0.4),          # r > 64: two column tiles per block
-                                                (64, 1, 80, "matern32", 0.4),     # same, ill-conditioned (floor applies)
-                                                (80, 2, 64, "exp", 0.4),          # the headline r
-                                                (72, 2, 33, "exp", 0.5),          # odd r: 8-byte copy path
-                                                (72, 2, 33, "matern32", 0.5),
-                                                (64, 1, 128, "exp", 0.3)])        # largest r of this build
-def test_large_r_against_oracle(n, M, r, family, frac):
-    """Knot counts no committed reference fixture covers, checked against the oracle on the same seeded inputs.
-    Tolerance: 1e-9 (likelihood relative, mean absolute on a unit-scale field, sd relative) or, where two
-    independent FP64 CPU evaluations of the same quantities (oracle recursion vs the dual-form NumPy model,
-    tests/_model.py) already differ by more, 20x that gap -- the conditioning noise floor."""
-    import pymra_b200.MRATools as mt
-    from _model import model_run
-    from oracle.mra_oracle import mra_oracle
+SEEDED = [
+    # dim, grid side / N, M, J, r, family, frac_obs
+    (2, 64, 1, -1, 80, "exp", 0.4),          # r > 64: two column tiles per block, leaves at level 1
+    (2, 64, 1, -1, 80, "matern32", 0.4),     # same, ill-conditioned
+    (2, 80, 2, -1, 64, "exp", 0.4),          # the headline r
+    (2, 72, 2, -1, 33, "exp", 0.5),          # odd r: 8-byte copy path
+    (2, 72, 2, -1, 33, "matern32", 0.5),
+    (2, 64, 1, -1, 128, "exp", 0.3),         # largest r of this build
+    (2, 64, 2, -1, 96, "exp", 0.4),          # r > 64 below level 1: T staging / two-tile GTF fold / multi-tile factors
+    (2, 64, 2, -1, 81, "matern32", 0.4),     # odd r > 64, two levels
+    (2, 72, 3, -1, 80, "exp", 0.4),          # r > 64, three levels
+    (1, 3000, 9, 2, 1, "exp", 0.4),          # 1-D, leaves at levels >= 8: second segment pass of k_predict_fused
+    (1, 20000, 8, 3, 2, "matern32", 0.1),    # same with even r (16-byte copies), 20 000 locations
+]
+
+
+@pytest.mark.parametrize("dim,n,M,J,r,family,frac", SEEDED)
+def test_seeded_cases_against_truth(dim, n, M, J, r, family, frac):
+    """Knot counts / depths no committed reference fixture covers: the CUDA path, the oracle port and the truth on
+    the same seeded inputs.  The port stands in for the reference (it is pinned to it on every fixture)."""
     from pymra_b200.MRATree import MRATree
-    locs = mt.genLocations2d(n)
-    rng = np.random.RandomState(n + r)
-    y = np.sin(6 * locs[:, :1]) * np.cos(4 * locs[:, 1:]) + 0.2 * rng.normal(size=(len(locs), 1))
-    obs = np.full_like(y, np.nan)
-    sel = np.sort(rng.choice(len(locs), int(frac * len(locs)), replace=False))
-    obs[sel] = y[sel]
-    l, sig, R = 0.3, 1.0, 1e-2
-    cov = (lambda a, b: mt.ExpCovFun(a, b, l=l)) if family == "exp" else (lambda a, b: mt.Matern32(a, b, l=l, sig=sig))
+    c = seeded_case(dim, n, M, J, r, family, frac)
     np.random.seed(7)
-    t = MRATree(locs, r, cov, obs, R, M=M)
+    t = MRATree(c["locs"], r, c["cov"], c["obs"], c["R"], M=M, J=J)
     lik = float(np.asarray(t.getLikelihood()).ravel()[0])
     mean, sd = t.predict()
-    np.random.seed(7)
-    o = mra_oracle(locs, r, family, l, sig, obs, R, M=M)
-    mod = model_run(t._structure, locs, obs, family, l, sig, R)
-    fl, fm, fs = errs(mod["lik"], mod["mean"], mod["sd"], o)
-    rl, em, es = errs(lik, mean, sd, o)
-    assert rl <= max(1e-9, 20 * fl), ("lik", rl, fl)
-    assert em <= max(1e-9, 20 * fm), ("mean", em, fm)
-    assert es <= max(1e-9, 20 * fs), ("sd", es, fs)
+    if dim == 1:
+        assert t._structure.depth >= 8                   # nseg = depth + 1 > MAXSEG
+    port = errs(c["oracle"]["lik"], c["oracle"]["mean"], c["oracle"]["sd"], c["truth"])
+    assert_close_to_truth((lik, mean, sd), port, c["truth"], (dim, n, M, r, family))
+    assert t._session.warnings() == 0
+
+
+# ---- the sizes BASELINE.json quotes: CUDA path vs the oracle port (no dense truth is possible at 250 000+ locations)
+FULLSIZE_TOL = {
+    # likelihood relative, mean absolute / field scale, sd relative.  ExpCovFun trees are well conditioned: 1e-9.
+    # Matern32 kappa = 0.3: the PORT's own inv()-noise dominates the sd difference (SURVEY.md 0.9 measured the
+    # reference at 1e-8 .. 7e-5 against itself under a 4-ulp perturbation); the bound is north_star's "1e-7 for the
+    # deepest trees" for likelihood and mean, and the port's noise level for sd.
+    "exp": (1e-9, 1e-9, 1e-9),
+    "matern32": (1e-9, 1e-7, 1e-4),
+}
+
+
+@pytest.mark.parametrize("case", ["cfg4", "cfg4_exp", "g700_r16_m7", "g700_r16_m7_exp"])
+def test_fullsize_against_port(case):
+    rec = fullsize_parity(case)
+    tl, tm, ts = FULLSIZE_TOL[FULLSIZE_CASES[case][3]]
+    assert rec["rng_state_equal"]                        # same RNG consumption as the port (hence the reference)
+    assert rec["lik_rel_err"] <= tl, rec
+    assert rec["mean_max_abs_err"] <= tm * max(1.0, rec["mean_scale"]), rec
+    assert rec["sd_max_rel_err"] <= ts, rec
+    assert rec["warnings"] == 0, rec
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("case", ["cfg3", "cfg3_exp"])
+def test_cfg3_against_port(case):
+    test_fullsize_against_port(case)
