@@ -44,7 +44,8 @@ enum mra_cov_family {      /* pyMRA/MRATools.py */
   MRA_COV_EXP = 0,         /* ExpCovFun  :265-269   exp(-D/l)                          */
   MRA_COV_MATERN32 = 1,    /* Matern32   :289-293   sig*(1+sqrt(3)D/l)*exp(-sqrt(3)D/l) */
   MRA_COV_MATERN52 = 2,    /* Matern52   :281-285   sig*(1+sqrt(5)D/l+5D^2/(3l^2))*exp(-sqrt(5)D/l) */
-  MRA_COV_GAUSSIAN = 3     /* GaussianCovFun :297-301  sig*exp(-D^2/(2 l^2)) */
+  MRA_COV_GAUSSIAN = 3,    /* GaussianCovFun :297-301  sig*exp(-D^2/(2 l^2)) */
+  MRA_COV_DENSE = 4        /* `cov` given as an N x N np.matrix (pyMRA/MRANode.py:73-75, 381-382); mra_set_cov_dense */
 };
 
 enum mra_node_kind { MRA_NODE_INTERNAL = 0, MRA_NODE_LEAF = 1, MRA_NODE_ORPHAN = 2 };
@@ -140,6 +141,10 @@ int mra_upload_data_dev(mra_handle *h, const double *dev_locs, const double *dev
  * nugget R (MRATree R / me_scale; must be a scalar, MRANode.py:85-88). */
 int mra_set_cov(mra_handle *h, int family, double length_scale, double sig);
 int mra_set_nugget(mra_handle *h, double R);
+/* `cov` as a dense N x N matrix (row-major, the caller's row order) already on the device and owned by the caller
+ * for as long as passes run (the reference slices it: cov[np.ix_(inds, kInds)], MRANode.py:73-75, 381-382).
+ * max_diag: its largest diagonal entry.  Meant for N <= ~1e4 (the matrix itself is 8 N^2 bytes). */
+int mra_set_cov_dense(mra_handle *h, const double *dev_cov, int64_t n, double max_diag);
 
 /* Prior pass + leaf terms + upward pass (MRANode.py:378-395, 403-480).
  * out[0] = root.d, out[1] = root.u; getLikelihood() = out[0] + out[1] (MRATree.py:82-84). */
@@ -213,6 +218,12 @@ int mra_last_flops(const mra_handle *h, double *likelihood_flops, double *predic
  * kernel family: "name total_ms launches algorithmic_flops_per_pass algorithmic_bytes_per_pass". */
 int mra_profile_enable(mra_handle *h, int on);
 int mra_profile_read(mra_handle *h, char *buf, size_t buflen);
+
+/* Opt-in diagnostics (pyMRA/MRATree.py:445-511 getBasisFunctionsMatrix needs per-node state the
+ * reference frees, MRANode.py:108-110).  keep_posterior_basis != 0: the next predict pass leaves the folded
+ * posterior basis t_j of EVERY level in the basis slab "V" (normally level 0's is consumed on the fly), from which
+ * pymra_b200/diagnostics.py rebuilds the reference's BTil blocks with the LINV / LPINV blocks of mra_debug_fetch. */
+int mra_set_diagnostics(mra_handle *h, int keep_posterior_basis);
 
 /* Test hook: copies an internal device buffer to the host.
  * what: "V" (N x ldv, node ignored), "A", "GT", "LPINV", "LINV", "VK" (per node), "dnode" (all nodes).

@@ -20,7 +20,8 @@
  *
  * Covariance families follow pyMRA/MRATools.py:229-245 (Euclidean distance), :265-269 (ExpCovFun),
  * :289-293 (Matern32), :281-285 (Matern52), :297-301 (GaussianCovFun), evaluated in the extended type from the
- * same double-precision inputs.
+ * same double-precision inputs; family 4 reads a dense N x N double matrix (`cov` given as np.matrix,
+ * pyMRA/MRANode.py:73-75, 381-382).
  *
  * Build: oracle/build_truth.sh (gcc -O2 -fopenmp -shared -fPIC [-DUSE_QUAD]).
  */
@@ -117,7 +118,7 @@ static int cholesky(real* a, int64_t n, int64_t ld) {
 /* Returns 0 on success, 1 + node index when that node's kInv is not positive definite, -1 when the dense
  * system is not, -2 on allocation failure. */
 int TRUTH_FN(int N, int dim, const double* locs, const double* obs, double R_in, int family, double l_in,
-             double sig_in, int n_nodes, const int32_t* node_parent, const int64_t* rows_off, const int32_t* rows,
+             double sig_in, const double* dense /* family 4: N x N covariance matrix, else NULL */, int n_nodes, const int32_t* node_parent, const int64_t* rows_off, const int32_t* rows,
              const int64_t* knots_off, const int32_t* knots, double* out_lik, double* out_mean, double* out_sd) {
   const real l = (real)l_in, sig = (real)sig_in, R = (real)R_in;
   Node* nd = (Node*)calloc((size_t)n_nodes, sizeof(Node));
@@ -170,7 +171,8 @@ int TRUTH_FN(int N, int dim, const double* locs, const double* obs, double R_in,
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < nr; ++i)
       for (int k = 0; k < nk; ++k)
-        B[(size_t)i * nk + k] = cov_eval(family, l, sig, locs + (size_t)q->rows[i] * dim, locs + (size_t)q->knots[k] * dim, dim);
+        B[(size_t)i * nk + k] = family == 4 ? (real)dense[(size_t)q->rows[i] * N + q->knots[k]]      /* MRANode.py:73-75, 381-382 */
+                                            : cov_eval(family, l, sig, locs + (size_t)q->rows[i] * dim, locs + (size_t)q->knots[k] * dim, dim);
     {
       /* local indices of this node's rows / knots inside every ancestor, by chaining idx_in_parent */
       int* ri = (int*)malloc(sizeof(int) * (size_t)nr);

@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-_FAM = {"exp": 0, "matern32": 1, "matern52": 2, "gaussian": 3}
+_FAM = {"exp": 0, "matern32": 1, "matern52": 2, "gaussian": 3, "dense": 4}
 _libs = {}
 
 
@@ -31,7 +31,7 @@ def _lib(precision):
         fn = getattr(lib, "mra_dense_truth_%s" % precision)
         fn.restype = C.c_int
         fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double,
-                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                        C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         _libs[precision] = fn
     return _libs[precision]
@@ -52,7 +52,7 @@ def tree_arrays(nodes):
     return parent, rows_off, cat(rows), knots_off, cat(knots)
 
 
-def dense_truth(locs, obs, R, family, l, sig, nodes, precision="l"):
+def dense_truth(locs, obs, R, family, l, sig, nodes, precision="l", cov_matrix=None):
     locs = np.ascontiguousarray(np.asarray(locs, dtype=np.float64))
     if locs.ndim == 1:
         locs = locs.reshape(-1, 1)
@@ -63,7 +63,12 @@ def dense_truth(locs, obs, R, family, l, sig, nodes, precision="l"):
     mean = np.empty(N)
     sd = np.empty(N)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = _lib(precision)(N, dim, p(locs), p(obs), float(R), _FAM[family], float(l), float(sig), len(parent),
+    dense = None
+    if family == "dense":
+        dense = np.ascontiguousarray(np.asarray(cov_matrix, dtype=np.float64))
+        assert dense.shape == (N, N)
+    rc = _lib(precision)(N, dim, p(locs), p(obs), float(R), _FAM[family], float(l), float(sig),
+                         p(dense) if dense is not None else None, len(parent),
                          p(parent), p(rows_off), p(rows), p(knots_off), p(knots), C.byref(lik), p(mean), p(sd))
     if rc != 0:
         raise np.linalg.LinAlgError("dense truth failed (code %d: >0 = node whose kInv is not SPD, -1 = dense "

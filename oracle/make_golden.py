@@ -97,9 +97,16 @@ def make_cov(family, l, sig):
     raise ValueError(family)
 
 
+def dense_recipe(locs, l, sig):
+    """A non-stationary covariance that only exists as a matrix: sig * s_i s_j exp(-D_ij / l), s = 1 + 0.3 sin(4x) cos(3y)
+    (tests/_util.py restates it; the N x N matrix itself is not stored in the fixture)."""
+    s = 1.0 + 0.3 * np.sin(4.0 * locs[:, 0]) * np.cos(3.0 * locs[:, -1])
+    return np.matrix(sig * (s[:, None] * s[None, :]) * np.asarray(mt.ExpCovFun(locs, locs, l=l)))
+
+
 def run_case(name, locs, obs, r, R, family, l, sig=1.0, M=-1, J=-1, critDepth=-1, seed=5,
-             note="", positional_M=None):
-    cov = make_cov(family, l, sig)
+             note="", positional_M=None, record_basis=False):
+    cov = dense_recipe(locs, l, sig) if family == "dense" else make_cov(family, l, sig)
     np.random.seed(seed)
     t0 = time.time()
     with Recorder() as rec:
@@ -109,6 +116,11 @@ def run_case(name, locs, obs, r, R, family, l, sig=1.0, M=-1, J=-1, critDepth=-1
             tree = MRATree(locs, r, cov, obs, R, M=M, J=J, critDepth=critDepth)
         lik = float(np.asarray(tree.getLikelihood()).ravel()[0])
         xP, sdP = tree.predict()
+        basis = {}
+        if record_basis:      # MRATree.py:445-511 as the unmodified reference returns it (children are deleted: root only)
+            for key, distr, kc in (("bf_prior", "prior", False), ("bf_prior_kc", "prior", True),
+                                   ("bf_post", "posterior", False), ("bf_post_kc", "posterior", True)):
+                basis[key] = np.asarray(tree.getBasisFunctionsMatrix(distr=distr, timesKC=kc), dtype=np.float64)
     dt = time.time() - t0
     st = rec.flatten() if "r" in rec.nodes and critDepth < 0 or critDepth > tree.M else None
     out = dict(locs=np.asarray(locs, dtype=np.float64), obs=np.asarray(obs, dtype=np.float64),
@@ -120,6 +132,7 @@ def run_case(name, locs, obs, r, R, family, l, sig=1.0, M=-1, J=-1, critDepth=-1
                ref_seconds=dt)
     if st is not None:
         out.update(st)
+    out.update(basis)
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **out)
@@ -299,6 +312,27 @@ def m0_dense():
     locs, obs = grid_case(20, 20, 0.5, 10)
     run_case("m0_dense", locs, obs, 4, 1e-2, "exp", 0.3, 1.0, M=0, seed=5,
              note="M=0: root is a leaf, exact GP")
+
+
+@case
+def g40_dense():
+    locs, obs = grid_case(40, 40, 0.4, 13)
+    run_case("g40_dense", locs, obs, 6, 2e-2, "dense", 0.25, 1.3, M=2, seed=5, record_basis=True,
+             note="cov given as an N x N np.matrix (MRANode.py:73-75, 381-382), SURVEY 8f.3; root basis functions recorded")
+
+
+@case
+def b1d_basis():
+    locs, y_obs, R, kappa = readme_1d("matern32")
+    run_case("b1d_basis", locs, y_obs, 2, R, "exp", kappa, 1.0, M=3, J=3, critDepth=4, seed=5, record_basis=True,
+             note="ka1e inputs with getBasisFunctionsMatrix outputs recorded (MRATree.py:445-511), SURVEY 8f.4")
+
+
+@case
+def g32_basis():
+    locs, obs = grid_case(32, 32, 0.4, 14)
+    run_case("g32_basis", locs, obs, 5, 1e-2, "matern32", 0.4, 1.0, M=2, seed=5, record_basis=True,
+             note="2-D case with getBasisFunctionsMatrix outputs recorded, SURVEY 8f.4")
 
 
 @case

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from _util import golden_names, load_golden, oracle_for  # noqa: E402
+from _util import dense_recipe, golden_names, load_golden, oracle_for  # noqa: E402
 from oracle.dense_truth import dense_truth  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "truth")
@@ -28,8 +28,9 @@ def truth_for(g, precision=None):
     N = len(g["locs"])
     if precision is None:
         precision = "q" if N <= 2600 else "l"
+    cm = dense_recipe(g["locs"], float(g["l"]), float(g["sig"])) if str(g["family"]) == "dense" else None
     t = dense_truth(g["locs"], g["obs"], float(g["R"]), str(g["family"]), float(g["l"]), float(g["sig"]),
-                    o["nodes"], precision)
+                    o["nodes"], precision, cov_matrix=cm)
     return t, o
 
 

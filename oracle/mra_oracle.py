@@ -187,9 +187,12 @@ def _rows_of_ancestor_B(node, l):
 
 def _prior(ctx, node):
     """B = residual covariance (rows x knots), kInv, k (MRANode.py:73-80, 378-395; App. A1)."""
-    X = ctx.locs[node.rows]
-    K = X[node.kInds]
-    B = ctx.cov(X, K)
+    if ctx.dense is not None:                 # `cov` given as an np.matrix: slices of it (MRANode.py:73-75, 381-382)
+        B = ctx.dense[np.ix_(node.rows, node.rows[node.kInds])]
+    else:
+        X = ctx.locs[node.rows]
+        K = X[node.kInds]
+        B = ctx.cov(X, K)
     chain = []
     anc = node.parent
     while anc is not None:
@@ -317,7 +320,12 @@ def _build(ctx, parent, ID, rows, nk_local, levels_left):
                 np.random.set_state(state)
     _posterior(ctx, node)
     if ctx.record is not None:
-        ctx.record.append(dict(ID=ID, rows=rows, kInds=node.kInds, leaf=node.leaf, d=node.d, u=node.u))
+        rec = dict(ID=ID, rows=rows, kInds=node.kInds, leaf=node.leaf, d=node.d, u=node.u)
+        if ctx.record_full:       # what MRATree.getBasisFunctionsMatrix reads from a node (MRATree.py:445-511)
+            W, U = np.linalg.eigh(node.kTil)
+            rec.update(B=node.B.copy(), BTil=np.array(node.BTil[node.res]), kC=np.linalg.cholesky(node.k),
+                       kTilC=U * np.sqrt(np.abs(W))[None, :])
+        ctx.record.append(rec)
     for ch in node.children:      # release the subtree, as MRANode.py:108-110 does
         ch.B = ch.BTil = ch.A = ch.ATil = None
     node.children = []
@@ -340,7 +348,7 @@ def _forked_child(ctx, parent, chID, rows, nk_local, levels_left, pipe, n_siblin
 
 
 def mra_oracle(locs, r, family, l, sig, obs, R, M=-1, J=-1, critDepth=-1, logdet="slogdet",
-               record=False, processes=False):
+               record=False, processes=False, cov_matrix=None):
     """Restatement of MRATree(locs, r, cov, obs, R, M, J, critDepth) + getLikelihood() + predict().
 
     Consumes the global NumPy RNG exactly like the reference.  processes=True runs the children of the
@@ -357,9 +365,15 @@ def mra_oracle(locs, r, family, l, sig, obs, R, M=-1, J=-1, critDepth=-1, logdet
     ctx.obs = np.asarray(obs, dtype=np.float64).reshape(-1)
     ctx.r, ctx.J, ctx.d, ctx.R = r, J, d, float(R)
     ctx.critDepth = critDepth
-    ctx.cov = make_cov(family, l, sig)
+    ctx.dense = None
+    if family == "dense":                     # the N x N covariance over the rows of locs instead of a closure
+        ctx.dense = np.asarray(cov_matrix, dtype=np.float64)
+        ctx.cov = None
+    else:
+        ctx.cov = make_cov(family, l, sig)
     ctx.logdet = logdet
     ctx.record = [] if record else None
+    ctx.record_full = record == "full"
     ctx.processes = bool(processes)        # True: really fork one process per child at critDepth (MRANode.py:90-104)
     root = _build(ctx, None, "r", np.arange(N, dtype=np.int64), np.arange(N, dtype=np.int64), M)
     out = dict(lik=float(root.d + root.u), d=float(root.d), u=float(root.u),

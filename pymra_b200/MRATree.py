@@ -77,6 +77,8 @@ class _Root(object):
         """The root's prior basis cov(locs, knots) (MRANode.py:384; no ancestors to condition on), evaluated with the
         caller's closure on first use -- what callers of the reference read from tree.root.B."""
         t = self._tree
+        if isinstance(t._cov_closure, np.ndarray):          # dense covariance matrix: a column slice (MRANode.py:381-382)
+            return np.matrix(np.asarray(t._cov_closure)[:, self.kInds])
         X = np.asarray(t.locs, dtype=np.float64).reshape(t._N, t.d)
         return np.matrix(t._cov_closure(X, X[self.kInds]))
 
@@ -115,7 +117,7 @@ class MRATree(object):
         self._obs_ref = obs
         self._obs_inds = None
         self._cov_closure = cov
-        self._cov = introspect(cov, self.d)
+        self._cov = introspect(cov, self.d, n_locs=N)
         self._R = float(R)
         logger.debug("r: %d, \tJ: %d,\tM: %d" % (self.r, self.J, self.M))
         logger.debug("mode: %s" % ("serial" if critDepth > self.M else "parallel"))
@@ -272,13 +274,21 @@ class MRATree(object):
         mean, sd = self._moments()
         return mean, sd
 
+    def getBasisFunctionsMatrix(self, distr="prior", groupByResolution=False, order="root", timesKC=False,
+                                all_levels=False):
+        """MRATree.py:445-511.  On a finished tree the reference only has the root left (children are deleted,
+        MRANode.py:108-110), which is what all_levels=False returns; all_levels=True assembles every resolution
+        from the state kept on the device (pymra_b200/diagnostics.py).  Diagnostic: not on the hot path."""
+        from .diagnostics import basis_functions_matrix
+        return basis_functions_matrix(self, distr, groupByResolution, order, timesKC, all_levels)
+
     # ---- beyond the reference: frozen-structure re-evaluation for MLE loops (SURVEY.md 8f.1)
     def refit(self, cov=None, R=None):
         """Re-evaluate likelihood (and, lazily, predictions) for new covariance parameters / nugget
         on the SAME tree structure and device-resident data."""
         if cov is not None:
             self._cov_closure = cov
-            self._cov = introspect(cov, self.d)
+            self._cov = introspect(cov, self.d, n_locs=self._N)
         if R is not None:
             if isinstance(R, bool) or not isinstance(R, (int, float, np.integer, np.floating)):
                 raise TypeError("R must be a real scalar")

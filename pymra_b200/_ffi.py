@@ -13,7 +13,7 @@ MRA_OK = 0
 STATUS_NAMES = {0: "MRA_OK", -1: "MRA_ERR_ARG", -2: "MRA_ERR_CUDA", -3: "MRA_ERR_STATE",
                 -4: "MRA_ERR_NOT_SPD", -5: "MRA_ERR_NOMEM"}
 WARN_NEGATIVE_VARIANCE = 2
-COV_EXP, COV_MATERN32, COV_MATERN52, COV_GAUSSIAN = 0, 1, 2, 3
+COV_EXP, COV_MATERN32, COV_MATERN52, COV_GAUSSIAN, COV_DENSE = 0, 1, 2, 3, 4
 
 _p32 = C.POINTER(C.c_int32)
 _p64 = C.POINTER(C.c_int64)
@@ -49,6 +49,7 @@ SIGNATURES = {
     "mra_upload_data_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mra_set_cov": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "mra_set_nugget": (C.c_int, [C.c_void_p, C.c_double]),
+    "mra_set_cov_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double]),
     "mra_run_likelihood": (C.c_int, [C.c_void_p, C.c_void_p, _pd]),
     "mra_run_predict": (C.c_int, [C.c_void_p, C.c_void_p, _pd, _pd]),
     "mra_run_likelihood_async": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "mra_stream_my_parts": (C.c_int, [C.c_void_p, _p32]),
     "mra_stream_end_local_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mra_stream_sync_knots": (C.c_int, [C.c_void_p, C.c_void_p, _p64]),
+    "mra_set_diagnostics": (C.c_int, [C.c_void_p, C.c_int]),
     "mra_last_warnings": (C.c_int, [C.c_void_p, _p32]),
     "mra_last_launches": (C.c_int, [C.c_void_p, _p64]),
     "mra_last_flops": (C.c_int, [C.c_void_p, _pd, _pd]),

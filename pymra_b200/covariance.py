@@ -2,7 +2,9 @@
 
 The reference takes `cov` as an arbitrary Python callable `(locs1, locs2) -> np.matrix`
 (pyMRA/MRANode.py:77-80, 384).  The device evaluates two families, mt.ExpCovFun and mt.Matern32
-(pyMRA/MRATools.py:265-269, 289-293), possibly scaled by a constant.  The closure is probed
+(pyMRA/MRATools.py:265-269, 289-293), possibly scaled by a constant (also Matern52 / GaussianCovFun), and the
+reference's other form of `cov`, a dense N x N np.matrix (pyMRA/MRANode.py:73-75, 381-382), which is copied to
+the device and looked up.  The closure is probed
 numerically, its family and parameters are recovered in closed form, and the result is verified
 on random location pairs; anything that does not verify raises (there is no CPU fallback).
 """
@@ -10,18 +12,21 @@ import math
 
 import numpy as np
 
-from ._ffi import COV_EXP, COV_GAUSSIAN, COV_MATERN32, COV_MATERN52
+from ._ffi import COV_DENSE, COV_EXP, COV_GAUSSIAN, COV_MATERN32, COV_MATERN52
 
 _S3 = math.sqrt(3.0)
 _S5 = math.sqrt(5.0)
-_NAMES = {COV_EXP: "exp", COV_MATERN32: "matern32", COV_MATERN52: "matern52", COV_GAUSSIAN: "gaussian"}
+_NAMES = {COV_EXP: "exp", COV_MATERN32: "matern32", COV_MATERN52: "matern52", COV_GAUSSIAN: "gaussian",
+          COV_DENSE: "dense"}
+DENSE_MAX_N = 20000      # 8 N^2 bytes of device memory: 3.2 GB
 
 
 class CovDescriptor(object):
-    __slots__ = ("family", "l", "sig")
+    __slots__ = ("family", "l", "sig", "matrix")
 
-    def __init__(self, family, l, sig=1.0):
+    def __init__(self, family, l, sig=1.0, matrix=None):
         self.family, self.l, self.sig = int(family), float(l), float(sig)
+        self.matrix = matrix          # COV_DENSE: the N x N covariance as a C-contiguous float64 ndarray
 
     @property
     def name(self):
@@ -65,13 +70,22 @@ def _solve_matern_t(g, order=3):
     return 0.5 * (lo + hi)
 
 
-def introspect(cov, d, rtol=1e-12, n_check=192, seed=12345):
+def introspect(cov, d, rtol=1e-12, n_check=192, seed=12345, n_locs=None):
     """Return the CovDescriptor of `cov`, or raise ValueError / NotImplementedError."""
     if isinstance(cov, CovDescriptor):
         return cov
-    if isinstance(cov, np.ndarray):      # np.matrix included (MRANode.py:73-75, 381-382)
-        raise NotImplementedError("a dense covariance matrix as `cov` is outside the accelerated path; "
-                                  "pass an mt.ExpCovFun / mt.Matern32 closure")
+    if isinstance(cov, np.ndarray):      # np.matrix included: the reference slices it (MRANode.py:73-75, 381-382)
+        C = np.ascontiguousarray(np.asarray(cov, dtype=np.float64))
+        if C.ndim != 2 or C.shape[0] != C.shape[1]:
+            raise ValueError("a covariance matrix passed as `cov` must be square (N x N over the rows of locs)")
+        if n_locs is not None and C.shape[0] != n_locs:
+            raise ValueError("the covariance matrix is %d x %d but there are %d locations" % (C.shape + (n_locs,)))
+        if C.shape[0] > DENSE_MAX_N:
+            raise NotImplementedError("a dense covariance matrix is supported up to N = %d locations" % DENSE_MAX_N)
+        dg = np.diag(C)
+        if not (np.all(np.isfinite(dg)) and np.all(dg > 0)):
+            raise ValueError("the covariance matrix needs a positive, finite diagonal")
+        return CovDescriptor(COV_DENSE, 1.0, float(np.max(dg)), matrix=C)
     if not callable(cov):
         raise TypeError("cov must be a callable (locs1, locs2) -> matrix")
     dists = np.array([0.0] + [10.0 ** e for e in np.arange(-4.0, 2.01, 0.25)])

@@ -45,7 +45,7 @@ struct Arena {
 
 struct Layout {
   size_t nodes, knot_rows, obs_rows, unobs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
-      mean, var, vnorm, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, ptiles, pgroups, gather, chunks, ltiles, GTF, UTF, fold, VKL;
+      mean, var, vnorm, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, ptiles, pgroups, gather, chunks, ltiles, GTF, UTF, fold, VKL, xidx;
   size_t total;
 };
 
@@ -75,6 +75,7 @@ struct mra_handle {
   std::vector<size_t> pgroups_off;             // per level offsets (bytes) inside lay.pgroups
   bool use_groups = true;
   bool chol_mma = true;
+  bool keep_t0 = false;
   std::vector<int4> leaf_tiles;                // 64-row tiles of leaves / orphans (fused predict pass)
   std::vector<int4> fold_items;                // (node, ancestor level, row tile, column tile) of k_fold
   std::vector<int2> emit_chunks;               // row ranges whose results this rank emits
@@ -109,7 +110,7 @@ struct mra_handle {
   size_t ws_bytes = 0;
   std::vector<size_t> list_off, ptiles_off;   // per level offsets (bytes) inside lay.lists / lay.ptiles
   size_t leaves_off = 0;
-  CovParams cov{0, 1.0, 1.0, 1.0, 1.0};
+  CovParams cov{0, 1.0, 1.0, 1.0, 1.0, nullptr, 0};
   double R = 1.0;
   bool cov_set = false, R_set = false;
   int64_t launches = 0;
@@ -196,8 +197,9 @@ DevCtx make_ctx(mra_handle* h) {
   c.unobs_rows = at<int>(h, L.unobs_rows);
   c.fill_qt = h->want_predict ? 1 : 0;
   c.gather_rows = at<int>(h, L.gather);
-  c.xs = at<double>(h, L.xs);
-  c.ys = at<double>(h, L.ys);
+  // dense covariance matrix: the kernels' "coordinates" are the locations' original row indices
+  c.xs = h->cov.family == MRA_COV_DENSE ? at<double>(h, L.xidx) : at<double>(h, L.xs);
+  c.ys = h->cov.family == MRA_COV_DENSE ? at<double>(h, L.xidx) : at<double>(h, L.ys);
   c.yobs = at<double>(h, L.yobs);
   c.V = at<double>(h, L.V);
   c.ldv = h->ldv;
@@ -223,6 +225,7 @@ DevCtx make_ctx(mra_handle* h) {
   c.cov = h->cov;
   c.R = h->R;
   c.chol_mma = h->chol_mma ? 1 : 0;
+  c.keep_t0 = h->keep_t0 ? 1 : 0;
   return c;
 }
 
@@ -1129,6 +1132,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.mean = ar.take(D * N);
   L.var = ar.take(D * N);
   L.vnorm = ar.take(D * N);
+  L.xidx = ar.take(D * N);
   L.status = ar.take(256);
   L.out = ar.take(256);
   L.stage_locs = ar.take(D * N * h->dim);
@@ -1237,7 +1241,7 @@ static int upload_impl(mra_handle* h, const double* locs, const double* obs, con
   }
   k_permute_inputs<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(
       dev_locs, dev_obs, at<int>(h, L.perm), (int)N, h->dim,
-      at<double>(h, L.xs), at<double>(h, L.ys), at<double>(h, L.yobs));
+      at<double>(h, L.xs), at<double>(h, L.ys), at<double>(h, L.yobs), at<double>(h, L.xidx));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(st));   // host vectors may change after return
   h->uploaded = true;
@@ -1259,12 +1263,29 @@ int mra_set_cov(mra_handle* h, int family, double length_scale, double sig) {
   if (!h) return MRA_ERR_ARG;
   if (family < MRA_COV_EXP || family > MRA_COV_GAUSSIAN) return fail(h, MRA_ERR_ARG, "unknown covariance family");
   if (!(length_scale > 0.0) || !(sig > 0.0)) return fail(h, MRA_ERR_ARG, "length scale and sig must be positive");
+  h->cov.dense = nullptr;
+  h->cov.n_dense = 0;
   h->cov.family = family;
   h->cov.l = length_scale;
   h->cov.sig = sig;
   h->cov.c0 = h->cov.sig;
   if (family == MRA_COV_GAUSSIAN) h->cov.a = 1.0 / (2.0 * length_scale * length_scale);
   else h->cov.a = (family == MRA_COV_EXP ? 1.0 : family == MRA_COV_MATERN32 ? 1.7320508075688772 : 2.23606797749979) / length_scale;
+  h->cov_set = true;
+  h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+int mra_set_cov_dense(mra_handle* h, const double* dev_cov, int64_t n, double max_diag) {
+  if (!h || !dev_cov) return MRA_ERR_ARG;
+  if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
+  if (n != h->N) return fail(h, MRA_ERR_ARG, "the dense covariance matrix must be N x N");
+  if (!(max_diag > 0.0)) return fail(h, MRA_ERR_ARG, "the covariance matrix needs a positive diagonal");
+  h->cov.family = MRA_COV_DENSE;
+  h->cov.l = h->cov.sig = h->cov.a = 1.0;
+  h->cov.c0 = max_diag;
+  h->cov.dense = dev_cov;
+  h->cov.n_dense = n;
   h->cov_set = true;
   h->lik_done = h->pred_done = false;
   return MRA_OK;
@@ -1527,6 +1548,13 @@ int mra_run_predict(mra_handle* h, void* stream, double* mean, double* sd) {
   CU(cudaMemcpyAsync(mean, h->ws + h->lay.out_mean, sizeof(double) * h->N, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(sd, h->ws + h->lay.out_sd, sizeof(double) * h->N, cudaMemcpyDeviceToHost, st));
   return check_status(h, st);
+}
+
+int mra_set_diagnostics(mra_handle* h, int keep_posterior_basis) {
+  if (!h) return MRA_ERR_ARG;
+  h->keep_t0 = keep_posterior_basis != 0;
+  h->pred_done = false;
+  return MRA_OK;
 }
 
 int mra_last_warnings(const mra_handle* h, int32_t* flags) {

@@ -116,7 +116,16 @@ class DeviceSession(object):
         self.check(self.lib.mra_upload_data(self.h, _dptr(locs_c), _dptr(obs_c), self.stream()))
 
     def set_params(self, cov, R):
-        self.check(self.lib.mra_set_cov(self.h, cov.family, cov.l, cov.sig))
+        if cov.family == _ffi.COV_DENSE:
+            import torch
+            if getattr(self, "_dense_src", None) is not cov.matrix:      # the same matrix stays resident across refits
+                self._dense = torch.from_numpy(cov.matrix).to(self.dev)
+                self._dense_src = cov.matrix
+            self.check(self.lib.mra_set_cov_dense(self.h, C.c_void_p(self._dense.data_ptr()), cov.matrix.shape[0],
+                                                  float(cov.sig)))
+        else:
+            self._dense = self._dense_src = None
+            self.check(self.lib.mra_set_cov(self.h, cov.family, cov.l, cov.sig))
         self.check(self.lib.mra_set_nugget(self.h, float(R)))
 
     # ---- passes
@@ -239,6 +248,10 @@ class DeviceSession(object):
                 raise ValueError("reduce=True needs caller-owned output tensors")
             dist.all_reduce(mean_t, group=self.group)
             dist.all_reduce(sd_t, group=self.group)
+
+    def keep_posterior_basis(self, on=True):
+        """Diagnostics (pymra_b200/diagnostics.py): the next predict pass keeps every level's folded posterior basis."""
+        self.check(self.lib.mra_set_diagnostics(self.h, 1 if on else 0))
 
     # ---- counters
     def warnings(self):

@@ -9,8 +9,18 @@ from conftest import GOLDEN, golden_names, load_golden, load_truth  # noqa: F401
 warnings.filterwarnings("ignore", category=DeprecationWarning)
 
 
+def dense_recipe(locs, l, sig):
+    """The matrix-only covariance of the `dense` fixtures (oracle/make_golden.py's dense_recipe, restated)."""
+    import pymra_b200.MRATools as mt
+    locs = np.asarray(locs, dtype=np.float64)
+    s = 1.0 + 0.3 * np.sin(4.0 * locs[:, 0]) * np.cos(3.0 * locs[:, -1])
+    return np.matrix(sig * (s[:, None] * s[None, :]) * np.asarray(mt.ExpCovFun(locs, locs, l=l)))
+
+
 def oracle_for(g, **kw):
     from oracle.mra_oracle import mra_oracle
+    if str(g["family"]) == "dense":
+        kw["cov_matrix"] = dense_recipe(g["locs"], float(g["l"]), float(g["sig"]))
     np.random.seed(int(g["seed"]))
     return mra_oracle(g["locs"], int(g["r"]), str(g["family"]), float(g["l"]), float(g["sig"]), g["obs"],
                       float(g["R"]), M=int(g["M_req"]), J=int(g["J_req"]), critDepth=int(g["critDepth"]), **kw)
@@ -29,6 +39,8 @@ def make_cov(g):
     import pymra_b200.MRATools as mt
     l, sig = float(g["l"]), float(g["sig"])
     fam = str(g["family"])
+    if fam == "dense":
+        return dense_recipe(g["locs"], l, sig)
     if fam == "exp":
         return lambda a, b: mt.ExpCovFun(a, b, l=l)
     if fam == "matern52":

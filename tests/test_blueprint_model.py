@@ -10,6 +10,8 @@ from test_oracle_golden import LOOSE
 @pytest.mark.parametrize("name", golden_names())
 def test_blueprint_matches_reference(name):
     g = load_golden(name)
+    if str(g["family"]) == "dense":
+        pytest.skip("the blueprint evaluates covariance closures; the matrix form is covered by tests/test_gpu_features.py")
     st = structure_for(g)
     o = model_run(st, g["locs"], g["obs"], str(g["family"]), float(g["l"]), float(g["sig"]), float(g["R"]))
     rl, em, es = errs(o["lik"], o["mean"], o["sd"], g)

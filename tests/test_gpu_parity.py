@@ -139,4 +139,13 @@ def test_fullsize_against_port(case):
 @pytest.mark.slow
 @pytest.mark.parametrize("case", ["cfg3", "cfg3_exp"])
 def test_cfg3_against_port(case):
-    test_fullsize_against_port(case)
+    """BASELINE configs[2] exactly (1000 x 1000, r0 = 32, M 8 -> 7); 40 s of port time per case.  The Matern32 sd bound
+    is the port's noise at this depth (measured 1.7e-4; at 15 625 locations the same port is 2.5e-5 from the dense
+    truth while the CUDA path is 1.4e-12 from it, profiles/r04_parity_table.md)."""
+    rec = fullsize_parity(case)
+    tl, tm, ts = FULLSIZE_TOL[FULLSIZE_CASES[case][3]]
+    if FULLSIZE_CASES[case][3] == "matern32":
+        ts = 1e-3
+    assert rec["rng_state_equal"] and rec["warnings"] == 0, rec
+    assert rec["lik_rel_err"] <= tl and rec["mean_max_abs_err"] <= tm * max(1.0, rec["mean_scale"]), rec
+    assert rec["sd_max_rel_err"] <= ts, rec

@@ -52,8 +52,12 @@ def test_cov_introspection(d):
     assert c.name == "gaussian" and abs(c.l - np.sqrt(0.5)) < 1e-13
     with pytest.raises(ValueError):
         introspect(lambda a, b: 1.0 / (1.0 + np.square(mt.dist(a, b))), d)     # rational quadratic: not supported
-    with pytest.raises(NotImplementedError):
-        introspect(np.matrix(np.eye(3)), d)
+    c = introspect(np.matrix(2.0 * np.eye(3)), d, n_locs=3)                    # dense matrix form (MRANode.py:73-75)
+    assert c.name == "dense" and c.sig == 2.0 and c.matrix.shape == (3, 3)
+    with pytest.raises(ValueError):
+        introspect(np.matrix(np.eye(3)), d, n_locs=4)
+    with pytest.raises(ValueError):
+        introspect(np.matrix(np.ones((3, 2))), d)
 
 
 def test_capi_exports_every_declared_symbol():

@@ -9,7 +9,7 @@ reference's own FP64 result is from exact arithmetic -- the yard
 import numpy as np
 import pytest
 
-from _util import errs, golden_names, load_golden, load_truth, oracle_for
+from _util import dense_recipe, errs, golden_names, load_golden, load_truth, oracle_for
 
 # likelihood relative, mean absolute, sd relative
 TIGHT = (1e-10, 2e-9, 5e-8)      # exponential covariance: everything is round-off
@@ -42,8 +42,9 @@ def test_committed_truth_is_reproducible_in_both_precisions(name):
     T = load_truth(name)
     o = oracle_for(g, record=True)
     for prec in ("l", "q"):
+        cm = dense_recipe(g["locs"], float(g["l"]), float(g["sig"])) if str(g["family"]) == "dense" else None
         t = dense_truth(g["locs"], g["obs"], float(g["R"]), str(g["family"]), float(g["l"]), float(g["sig"]),
-                        o["nodes"], prec)
+                        o["nodes"], prec, cov_matrix=cm)
         rl, em, es = errs(t["lik"], t["mean"], t["sd"], T)
         assert rl <= 1e-14 and em <= 1e-14 * max(1.0, float(np.max(np.abs(T["mean"])))) and es <= 1e-13, (prec, rl, em, es)
 
