@@ -160,6 +160,15 @@ int mra_run_likelihood_async(mra_handle *h, void *stream);
 int mra_run_predict_dev(mra_handle *h, void *stream, double *dev_mean, double *dev_sd);
 int mra_fetch_likelihood(mra_handle *h, void *stream, double out[2]);
 
+/* One whole evaluation on the frozen tree as ONE CUDA graph launch (the Nelder-Mead loop of README.md:96-104
+ * re-evaluates the likelihood ~100 times on the same tree): the first call captures the launches of
+ * mra_run_likelihood_async (and, with_predict != 0, of mra_run_predict_dev into the handle's own result buffers), later
+ * calls replay them.  mra_set_cov / mra_set_nugget between calls take effect: the covariance descriptor and the nugget are
+ * read by the kernels from a parameter block in device memory that is refreshed before every launch.  Anything that
+ * changes the work lists or the buffers (structure, plan, workspace, sharding, diagnostics, dense <-> closure covariance)
+ * drops the graph; the next call captures again.  Same results, bit for bit, as the plain calls.  Unsharded handles only. */
+int mra_run_graph(mra_handle *h, void *stream, int with_predict);
+
 /* Multi-GPU subtree sharding (one process / handle per GPU).  Replaces the reference's fork-per-child
  * subtree mode (pyMRA/MRANode.py:90-104, 114-115: mp.Process per child at res == critDepth, the child Node
  * pickled back through a pipe) by one rank per GPU: subtrees rooted at `shard_level` are owned by exactly one

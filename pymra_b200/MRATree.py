@@ -242,9 +242,13 @@ class MRATree(object):
         return self._obs_inds
 
     # ---- plumbing
-    def _evaluate(self):
+    def _evaluate(self, graph=False):
         self._session.set_params(self._cov, self._R)
-        self._d, self._u = self._session.likelihood()
+        if graph and not self._session.shard_level:
+            self._session.likelihood_graph()
+            self._d, self._u = self._session.fetch_likelihood()
+        else:
+            self._d, self._u = self._session.likelihood()
         self._mom = None
 
     def _moments(self):
@@ -293,6 +297,6 @@ class MRATree(object):
             if isinstance(R, bool) or not isinstance(R, (int, float, np.integer, np.floating)):
                 raise TypeError("R must be a real scalar")
             self._R = float(R)
-        self._evaluate()
+        self._evaluate(graph=os.environ.get("PYMRA_B200_GRAPH", "1") != "0")      # one graph launch per evaluation
         self.root = _Root(self)
         return self.getLikelihood()

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <utility>
 #include <string>
 #include <thread>
@@ -45,7 +46,7 @@ struct Arena {
 
 struct Layout {
   size_t nodes, knot_rows, obs_rows, unobs_rows, perm, xs, ys, yobs, V, S, DI, UT, QT, A, GT, LPINV, VK, LINV, dnode,
-      mean, var, vnorm, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, ptiles, pgroups, gather, chunks, ltiles, GTF, UTF, fold, VKL, xidx;
+      mean, var, vnorm, status, out, stage_locs, stage_obs, out_mean, out_sd, lists, ptiles, pgroups, gather, chunks, ltiles, GTF, UTF, fold, VKL, xidx, LS, UTTN, params;
   size_t total;
 };
 
@@ -76,6 +77,16 @@ struct mra_handle {
   bool use_groups = true;
   bool chol_mma = true;
   bool keep_t0 = false;
+  bool leaf_v2 = true;
+  bool leaf_wide = true;
+  DevParams hparams{};
+  // CUDA graph of a whole evaluation on a frozen tree (mra_run_graph)
+  bool capturing = false;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int graph_predict = -1;
+  int64_t graph_launches = 0;
+  cudaStream_t gstream = nullptr;
   std::vector<int4> leaf_tiles;                // 64-row tiles of leaves / orphans (fused predict pass)
   std::vector<int4> fold_items;                // (node, ancestor level, row tile, column tile) of k_fold
   std::vector<int2> emit_chunks;               // row ranges whose results this rank emits
@@ -155,6 +166,14 @@ int fail(mra_handle* h, int code, const std::string& msg) {
   return code;
 }
 
+void drop_graph(mra_handle* h) {
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  if (h->graph) cudaGraphDestroy(h->graph);
+  h->gexec = nullptr;
+  h->graph = nullptr;
+  h->graph_predict = -1;
+}
+
 #define CU(call)                                                                                 \
   do {                                                                                           \
     cudaError_t e_ = (call);                                                                     \
@@ -195,7 +214,7 @@ DevCtx make_ctx(mra_handle* h) {
   c.knot_rows = at<int>(h, L.knot_rows);
   c.obs_rows = at<int>(h, L.obs_rows);
   c.unobs_rows = at<int>(h, L.unobs_rows);
-  c.fill_qt = h->want_predict ? 1 : 0;
+  c.fill_qt = (h->want_predict && !h->leaf_v2) ? 1 : 0;
   c.gather_rows = at<int>(h, L.gather);
   // dense covariance matrix: the kernels' "coordinates" are the locations' original row indices
   c.xs = h->cov.family == MRA_COV_DENSE ? at<double>(h, L.xidx) : at<double>(h, L.xs);
@@ -222,10 +241,12 @@ DevCtx make_ctx(mra_handle* h) {
   c.var = at<double>(h, L.var);
   c.vnorm = at<double>(h, L.vnorm);
   c.status = at<int>(h, L.status);
-  c.cov = h->cov;
-  c.R = h->R;
+  c.P = at<DevParams>(h, L.params);
   c.chol_mma = h->chol_mma ? 1 : 0;
   c.keep_t0 = h->keep_t0 ? 1 : 0;
+  c.leaf_v2 = h->leaf_v2 ? 1 : 0;
+  c.LS = at<double>(h, L.LS);
+  c.UTTN = at<double>(h, L.UTTN);
   return c;
 }
 
@@ -237,6 +258,13 @@ size_t smem_cholinv(int n) {     // the larger of the two chol_inv_block variant
 }
 size_t smem_prior(int r) { return sizeof(GemmSmemT<2>) + sizeof(double) * ((size_t)2 * r + 2 * TB) + sizeof(int) * TB; }
 size_t smem_pgroups(int r) { return sizeof(PriorSmem) + sizeof(double) * ((size_t)2 * r + 2 * PG * TB); }
+size_t smem_ut2(int max_obs) { return GS1 + sizeof(double*) * (size_t)((max_obs + TB - 1) / TB * TB); }
+size_t smem_leafq(int max_obs) {
+  return sizeof(GemmSmemT<2>) + sizeof(double) * ((size_t)3 * max_obs + 2 * TB) + sizeof(int) * TB + 16;
+}
+size_t smem_leafq2(int max_obs) {
+  return sizeof(WideSmem) + sizeof(double) * ((size_t)3 * max_obs + 2 * TB + 4 * TB) + sizeof(int) * TB + 16;
+}
 size_t smem_gram() { return GS1 + sizeof(int) * 2 * TB; }
 size_t smem_solve() { return GS1; }
 size_t smem_plain() { return sizeof(GemmSmemT<4>); }   // k_assemble_A: up to 4 children per product
@@ -256,6 +284,23 @@ size_t smem_predict(int r) {
       expr;                          \
     }                                \
   } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel and device, not per handle: several handles with different r
+// or leaf sizes live in one process (sharded emulation, tests, MLE over several trees), so the limit only ever grows.
+template <class K>
+cudaError_t smem_at_least(K kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> seen;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = seen[std::make_pair(dev, reinterpret_cast<const void*>(kernel))];
+  if (bytes <= cur) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
 
 // Kernels whose tile columns are the r knots of a node are also instantiated for narrow tiles (NJ 8-column groups,
 // mra_gemm.cuh): r0 = 16 / 32 (BASELINE cfg4 / cfg3) run 64 x 16 / 64 x 32 tiles instead of zero-padded 64 x 64 ones.
@@ -282,8 +327,8 @@ size_t smem_predict(int r) {
 template <int V_, int J_>
 cudaError_t configure_vec_nj(int r) {
   cudaError_t e;
-#define SET_(k, bytes)                                                                         \
-  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));      \
+#define SET_(k, bytes)              \
+  e = smem_at_least(k, (bytes));    \
   if (e != cudaSuccess) return e
   SET_((k_knot_gram<V_, J_>), smem_knot(r));
   SET_((k_prior_tiles<V_, J_>), smem_prior(r));
@@ -299,12 +344,15 @@ cudaError_t configure_vec_nj(int r) {
 template <int V_>
 cudaError_t configure_vec(int r, int max_obs) {
   cudaError_t e;
-#define SET_(k, bytes)                                                                         \
-  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));      \
+#define SET_(k, bytes)              \
+  e = smem_at_least(k, (bytes));    \
   if (e != cudaSuccess) return e
   SET_(k_knot_vkl<V_>, GS1);
   SET_(k_leaf_gram<V_>, smem_gram());
   SET_(k_leaf_upd<V_>, GS1);
+  SET_(k_leaf_linv<V_>, GS1);
+  SET_(k_leaf_ut2<V_>, smem_ut2(max_obs));
+  SET_(k_leaf_q<V_>, smem_leafq(max_obs));
   SET_(k_leaf_trsm<V_>, GS1);
   SET_(k_leaf_solve_ut<V_>, smem_solve());
   SET_(k_leaf_solve_qt<V_>, smem_solve());
@@ -318,9 +366,10 @@ cudaError_t configure_vec(int r, int max_obs) {
 int configure_kernels(mra_handle* h) {
   MRA_FOR_VEC(h, CU(configure_vec<V_>(h->r, h->max_leaf_obs)));
   MRA_FOR_VEC_NJ(h, CU((configure_vec_nj<V_, J_>(h->r))));
-  CU(cudaFuncSetAttribute(k_knot_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cholinv(h->r)));
-  CU(cudaFuncSetAttribute(k_node_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cholinv(h->r)));
-  CU(cudaFuncSetAttribute(k_leaf_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cholinv(TB)));
+  CU(smem_at_least(k_knot_chol, smem_cholinv(h->r)));
+  CU(smem_at_least(k_node_chol, smem_cholinv(h->r)));
+  CU(smem_at_least(k_leaf_chol, smem_cholinv(TB)));
+  CU(smem_at_least(k_leaf_q2, smem_leafq2(h->max_leaf_obs)));
   return MRA_OK;
 }
 
@@ -472,7 +521,14 @@ int leaf_terms(mra_handle* h, cudaStream_t st, const DevCtx& c, Range rg) {
       MRA_FOR_VEC(h, LAUNCH("leaf_trsm", k_leaf_trsm<V_><<<(unsigned)nleaf * (nbo - 1 - p), NT, GS1, st>>>(c, leaf_list, p, nbo - 1 - p)));
   }
   const int nt3 = std::max(1, (h->max_leaf_W - 1 + TB - 1) / TB);
-  MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve_ut<V_><<<(unsigned)nleaf * nt3, NT, smem_solve(), st>>>(c, leaf_list, nt3)));
+  if (h->leaf_v2) {
+    MRA_FOR_VEC(h, LAUNCH("leaf_linv", k_leaf_linv<V_><<<nleaf, NT, GS1, st>>>(c, leaf_list)));
+    if (h->max_leaf_W > 1)
+      MRA_FOR_VEC(h, LAUNCH("leaf_ut", k_leaf_ut2<V_><<<(unsigned)nleaf * nbo * nt3, NT, smem_ut2(h->max_leaf_obs), st>>>(
+                                           c, leaf_list, nbo * nt3, nt3)));
+  } else {
+    MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve_ut<V_><<<(unsigned)nleaf * nt3, NT, smem_solve(), st>>>(c, leaf_list, nt3)));
+  }
   return MRA_OK;
 }
 
@@ -484,6 +540,17 @@ int leaf_predict_terms(mra_handle* h, cudaStream_t st, const DevCtx& c, Range rg
   const int* leaf_list = reinterpret_cast<const int*>(h->ws + L.lists + h->leaves_off) + rg.begin;
   const int nbo = (h->max_leaf_obs + TB - 1) / TB, nbr = (h->max_leaf_rows + TB - 1) / TB;
   const int nbu = (h->max_leaf_unobs + TB - 1) / TB;
+  if (h->leaf_v2) {
+    if (nbu > 0) {
+      if (h->leaf_wide)
+        LAUNCH("leaf_q", k_leaf_q2<<<(unsigned)nleaf * nbu, NTW, smem_leafq2(h->max_leaf_obs), st>>>(c, leaf_list, nbu, h->max_leaf_obs));
+      else
+        MRA_FOR_VEC(h, LAUNCH("leaf_q", k_leaf_q<V_><<<(unsigned)nleaf * nbu, NT, smem_leafq(h->max_leaf_obs), st>>>(
+                                            c, leaf_list, nbu, h->max_leaf_obs)));
+    }
+    LAUNCH("leaf_qobs", k_leaf_qobs<<<nleaf, NT, 0, st>>>(c, leaf_list));
+    return MRA_OK;
+  }
   if (nbu > 0)
     MRA_FOR_VEC(h, LAUNCH("leaf_gram_T", k_leaf_gram<V_><<<(unsigned)nleaf * nbu * nbo, NT, smem_gram(), st>>>(
                                              c, leaf_list, 1, nleaf)));
@@ -492,8 +559,20 @@ int leaf_predict_terms(mra_handle* h, cudaStream_t st, const DevCtx& c, Range rg
   return MRA_OK;
 }
 
+// the parameter block of this pass (covariance descriptor, nugget) goes to the device ahead of its kernels
+int upload_params(mra_handle* h, cudaStream_t st) {
+  h->hparams.cov = h->cov;
+  h->hparams.R = h->R;
+  CU(cudaMemcpyAsync(h->ws + h->lay.params, &h->hparams, sizeof(DevParams), cudaMemcpyHostToDevice, st));
+  return MRA_OK;
+}
+
 int reset_pass(mra_handle* h, cudaStream_t st) {
   const Layout& L = h->lay;
+  if (!h->capturing) {
+    int rc = upload_params(h, st);
+    if (rc) return rc;
+  }
   h->launches = 0;
   h->warnings = 0;
   h->leafq_done = false;
@@ -594,7 +673,7 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
   }
   if (!h->emit_chunks.empty())
     LAUNCH("unpermute", k_unpermute<<<(unsigned)h->emit_chunks.size(), 256, 0, st>>>(
-                            c.mean, c.var, at<int>(h, L.perm), at<int2>(h, L.chunks), om, os, h->cov.c0, c.status));
+                            c.mean, c.var, at<int>(h, L.perm), at<int2>(h, L.chunks), om, os, c.P, c.status));
   CU(cudaGetLastError());
   return MRA_OK;
 }
@@ -807,6 +886,8 @@ int mra_create(mra_handle** out, int device) {
   h->device = device;
   h->use_groups = !(env_groups && env_groups[0] == '0');      // A/B switch for profiling (default: grouped prior tiles)
   if (const char* e = std::getenv("MRA_CHOL_MMA")) h->chol_mma = e[0] != '0';
+  if (const char* e = std::getenv("MRA_LEAF_V2")) h->leaf_v2 = e[0] != '0';
+  if (const char* e = std::getenv("MRA_LEAF_WIDE")) h->leaf_wide = e[0] != '0';
   {
     DevGuard g(device);          // validates the ordinal / creates the context; the caller's device is restored
     if (g.err != cudaSuccess) {
@@ -825,6 +906,8 @@ int mra_destroy(mra_handle* h) {
     cudaStreamDestroy(h->copy_stream);
   }
   if (h) {
+    drop_graph(h);
+    if (h->gstream) cudaStreamDestroy(h->gstream);
     for (auto& rec : h->prof_recs) {
       cudaEventDestroy(rec.e0);
       cudaEventDestroy(rec.e1);
@@ -905,9 +988,10 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
   const int nn = h->n_nodes, r = h->r;
   h->want_predict = want_predict != 0;
+  drop_graph(h);
   h->nodes.assign(nn, NodeDev{});
   long long s_off = 0, di_off = 0, ut_off = 0, qt_off = 0, a_off = 0, gt_off = 0, lp_off = 0, vk_off = 0,
-            linv_off = 0;
+            linv_off = 0, utt_off = 0;
   h->max_leaf_obs = h->max_leaf_rows = h->max_leaf_unobs = 0;
   h->max_leaf_W = 1;
   for (auto& f : h->kflops) f = 0.0;
@@ -1054,6 +1138,8 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       di_off += (long long)nb * TB * TB;
       d.ut_off = ut_off;
       ut_off += (long long)d.W * d.ldo;
+      d.utt_off = utt_off;
+      utt_off += (long long)d.n_obs * std::max(2, (d.W - 1 + 1) / 2 * 2);
       d.qt_off = qt_off;
       if (h->want_predict) qt_off += (long long)d.row_count * d.ldo;
       h->max_leaf_obs = std::max(h->max_leaf_obs, d.n_obs);
@@ -1067,12 +1153,27 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
         if (pb > 0) add_work(h, "leaf_upd", nv * nv * Kp, 8.0 * (nv * Kp + nv * nv));
         if (below > 0) add_work(h, "leaf_trsm", below * nv * (2.0 * Kp + nv), 8.0 * (below * (Kp + 2 * nv) + nv * Kp + nv * nv));
       }
-      add_work(h, "leaf_solve", no * no * W, 8.0 * (2 * no * W + no * no / 2));
+      if (h->leaf_v2) {
+        for (int bj = 0; (bj + 1) * TB < d.n_obs; ++bj)
+          for (int bi = bj + 1; bi * TB < d.n_obs; ++bi) {
+            const double nvi = std::min(TB, d.n_obs - bi * TB);
+            add_work(h, "leaf_linv", nvi * TB * TB * (bi - bj) + nvi * nvi * TB, 8.0 * (3.0 * nvi * TB + TB * TB * (bi - bj)));
+          }
+        add_work(h, "leaf_linv", 0.0, 8.0 * no * no);
+        add_work(h, "leaf_ut", no * no * Kv, 8.0 * (3 * no * Kv + no * no / 2));
+      } else {
+        add_work(h, "leaf_solve", no * no * W, 8.0 * (2 * no * W + no * no / 2));
+      }
       add_work(h, "assemble_A", W * W * no, 8.0 * no * W);
       if (d.kind == KIND_LEAF) {
         add_work(h, "predict_fused", 2.0 * nl * Kv, 8.0 * nl * (Kv + 2));
-        add_work(h, "leaf_gram_T", 2.0 * (nl - no) * no * Kv, 8.0 * ((nl + no) * Kv + nl * no));
-        add_work(h, "leaf_solve_Q", nl * no * no, 8.0 * (2 * nl * no + no * no / 2));
+        if (h->leaf_v2) {
+          add_work(h, "leaf_q", 2.0 * (nl - no) * no * Kv + (nl - no) * no * no, 8.0 * ((nl - no) * (Kv + no) + no * (Kv + no / 2)));
+          add_work(h, "leaf_qobs", 0.0, 8.0 * 2.0 * no * no);
+        } else {
+          add_work(h, "leaf_gram_T", 2.0 * (nl - no) * no * Kv, 8.0 * ((nl + no) * Kv + nl * no));
+          add_work(h, "leaf_solve_Q", nl * no * no, 8.0 * (2 * nl * no + no * no / 2));
+        }
         add_work(h, "predict_fused", 2.0 * nl * no * W + 2.0 * nl * no, 8.0 * (nl * no + no * W));
       }
     }
@@ -1100,7 +1201,8 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   h->flops_lik = h->flops_pred = 0.0;
   for (size_t i = 0; i < h->kname.size(); ++i) {
     const std::string& nm = h->kname[i];
-    const bool pred = nm == "leaf_gram_T" || nm == "leaf_solve_Q" || nm == "fold" || nm == "predict_fused" || nm == "unpermute";
+    const bool pred = nm == "leaf_gram_T" || nm == "leaf_solve_Q" || nm == "leaf_q" || nm == "leaf_qobs" || nm == "fold" ||
+                      nm == "predict_fused" || nm == "unpermute";
     (pred ? h->flops_pred : h->flops_lik) += h->kflops[i];
   }
   // ---- arena layout
@@ -1117,6 +1219,8 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.yobs = ar.take(D * N);
   L.V = ar.take(D * N * (size_t)h->ldv);
   L.S = ar.take(D * std::max<long long>(1, s_off));
+  L.LS = ar.take(D * std::max<long long>(1, h->leaf_v2 ? s_off : 0));
+  L.UTTN = ar.take(D * std::max<long long>(1, h->leaf_v2 ? utt_off : 0));
   L.DI = ar.take(D * std::max<long long>(1, di_off));
   L.UT = ar.take(D * std::max<long long>(1, ut_off));
   L.QT = ar.take(D * std::max<long long>(1, qt_off));
@@ -1134,6 +1238,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   L.vnorm = ar.take(D * N);
   L.xidx = ar.take(D * N);
   L.status = ar.take(256);
+  L.params = ar.take(256);
   L.out = ar.take(256);
   L.stage_locs = ar.take(D * N * h->dim);
   L.stage_obs = ar.take(D * N);
@@ -1178,6 +1283,7 @@ int mra_bind_workspace(mra_handle* h, void* dev_workspace, size_t bytes) {
   if (bytes < h->lay.total) return fail(h, MRA_ERR_NOMEM, "workspace smaller than mra_plan reported");
   if (reinterpret_cast<uintptr_t>(dev_workspace) % 256) return fail(h, MRA_ERR_ARG, "workspace must be 256-byte aligned");
   DEVICE_SCOPE(h);
+  drop_graph(h);
   h->ws = static_cast<char*>(dev_workspace);
   h->ws_bytes = bytes;
   int rc = configure_kernels(h);
@@ -1263,6 +1369,7 @@ int mra_set_cov(mra_handle* h, int family, double length_scale, double sig) {
   if (!h) return MRA_ERR_ARG;
   if (family < MRA_COV_EXP || family > MRA_COV_GAUSSIAN) return fail(h, MRA_ERR_ARG, "unknown covariance family");
   if (!(length_scale > 0.0) || !(sig > 0.0)) return fail(h, MRA_ERR_ARG, "length scale and sig must be positive");
+  if (h->cov.family == MRA_COV_DENSE) drop_graph(h);
   h->cov.dense = nullptr;
   h->cov.n_dense = 0;
   h->cov.family = family;
@@ -1281,6 +1388,7 @@ int mra_set_cov_dense(mra_handle* h, const double* dev_cov, int64_t n, double ma
   if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
   if (n != h->N) return fail(h, MRA_ERR_ARG, "the dense covariance matrix must be N x N");
   if (!(max_diag > 0.0)) return fail(h, MRA_ERR_ARG, "the covariance matrix needs a positive diagonal");
+  if (h->cov.family != MRA_COV_DENSE) drop_graph(h);      // the kernels' coordinate arrays change
   h->cov.family = MRA_COV_DENSE;
   h->cov.l = h->cov.sig = h->cov.a = 1.0;
   h->cov.c0 = max_diag;
@@ -1318,6 +1426,63 @@ int mra_run_likelihood_async(mra_handle* h, void* stream) {
   return launch_likelihood_top(h, static_cast<cudaStream_t>(stream), nullptr);
 }
 
+int mra_run_graph(mra_handle* h, void* stream, int with_predict) {
+  if (!h) return MRA_ERR_ARG;
+  if (h->shard_level > 0) return fail(h, MRA_ERR_STATE, "sharded handle: the exchange between the ranks cannot be captured");
+  if (h->profiling) return fail(h, MRA_ERR_STATE, "per-kernel profiling and graph replay exclude each other");
+  if (with_predict && !h->want_predict) return fail(h, MRA_ERR_STATE, "mra_plan was called with want_predict = 0");
+  DEVICE_SCOPE(h);
+  int rc = ready_to_run(h);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (st == nullptr || st == cudaStreamLegacy) {
+    // the legacy default stream cannot be captured: use an own (blocking) stream, which the legacy stream and every
+    // other blocking stream order themselves against implicitly
+    if (!h->gstream) CU(cudaStreamCreate(&h->gstream));
+    st = h->gstream;
+  }
+  with_predict = with_predict ? 1 : 0;
+  if (!h->gexec || h->graph_predict != with_predict) {
+    drop_graph(h);
+    h->capturing = true;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      rc = launch_likelihood_local(h, st, nullptr);
+      if (!rc) rc = launch_likelihood_top(h, st, nullptr);
+      if (!rc && with_predict) rc = launch_predict(h, st, nullptr, nullptr);
+      cudaGraph_t g = nullptr;
+      cudaError_t e2 = cudaStreamEndCapture(st, &g);
+      h->graph = g;
+      if (e2 != cudaSuccess) e = e2;
+    }
+    h->capturing = false;
+    if (rc) {
+      drop_graph(h);
+      return rc;
+    }
+    if (e != cudaSuccess) {
+      drop_graph(h);
+      return fail(h, MRA_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    }
+    h->graph_launches = h->launches;
+    e = cudaGraphInstantiate(&h->gexec, h->graph, 0);
+    if (e != cudaSuccess) {
+      drop_graph(h);
+      return fail(h, MRA_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    h->graph_predict = with_predict;
+  }
+  rc = upload_params(h, st);
+  if (rc) return rc;
+  CU(cudaGraphLaunch(h->gexec, st));
+  h->launches = h->graph_launches;
+  h->warnings = 0;
+  h->lik_done = true;
+  h->pred_done = with_predict != 0;
+  h->leafq_done = with_predict != 0;
+  return MRA_OK;
+}
+
 int mra_set_shard(mra_handle* h, int32_t shard_level, const int8_t* node_role) {
   if (!h) return MRA_ERR_ARG;
   if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
@@ -1336,6 +1501,7 @@ int mra_set_shard(mra_handle* h, int32_t shard_level, const int8_t* node_role) {
     h->shard_level = shard_level;
     h->role.assign(node_role, node_role + h->n_nodes);
   }
+  drop_graph(h);
   h->slot_base = shard_level ? h->level_off[shard_level] : 0;
   h->n_slots = shard_level ? h->level_off[shard_level + 1] - h->level_off[shard_level] : 0;
   build_lists(h);
@@ -1554,6 +1720,7 @@ int mra_set_diagnostics(mra_handle* h, int keep_posterior_basis) {
   if (!h) return MRA_ERR_ARG;
   h->keep_t0 = keep_posterior_basis != 0;
   h->pred_done = false;
+  drop_graph(h);
   return MRA_OK;
 }
 

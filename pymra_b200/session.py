@@ -142,6 +142,11 @@ class DeviceSession(object):
         dist.all_reduce(self.summary, group=self.group)       # disjoint slots: the sum is exact
         self.likelihood_top_async()
 
+    def likelihood_graph(self, with_predict=False):
+        """The whole likelihood pass (optionally + predict pass) as one CUDA graph launch; captured on first use and
+        after anything that changes the work lists.  Parameters set with set_params since the capture take effect."""
+        self.check(self.lib.mra_run_graph(self.h, self.stream(), 1 if with_predict else 0))
+
     def likelihood_local_async(self):
         """Sharded step 1: prior + leaves + upward pass of my subtrees; my summaries land in self.summary."""
         self.summary.zero_()

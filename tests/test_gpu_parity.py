@@ -67,6 +67,27 @@ def test_refit_equals_fresh_construction():
     assert np.array_equal(m, m2) and np.array_equal(s, s2)
 
 
+def test_refit_through_cuda_graph_is_bitwise_the_plain_pass(monkeypatch):
+    """MRATree.refit replays one captured CUDA graph per evaluation; the covariance parameters and the
+    nugget reach the kernels through the device parameter block, so new values take effect without a re-capture."""
+    import pymra_b200.MRATools as mt
+    g = load_golden("g96_m32_r16")
+    t = tree_for(g)
+    covs = [(lambda a, b, l=l: mt.Matern32(a, b, l=l, sig=1.0)) for l in (0.3, 0.22, 0.41, 0.3)]
+    monkeypatch.setenv("PYMRA_B200_GRAPH", "0")
+    plain = [float(t.refit(cov=c, R=R)) for c, R in zip(covs, (1e-2, 2e-2, 1e-2, 1e-2))]
+    mp, sp = t.predict()
+    monkeypatch.setenv("PYMRA_B200_GRAPH", "1")
+    graph = [float(t.refit(cov=c, R=R)) for c, R in zip(covs, (1e-2, 2e-2, 1e-2, 1e-2))]
+    mg, sg = t.predict()
+    assert plain == graph and len(set(plain)) == 3          # bitwise, and the parameters really changed the result
+    assert np.array_equal(np.asarray(mp), np.asarray(mg)) and np.array_equal(sp, sg)
+    assert t._session.launches() > 20
+    t._session.likelihood_graph(with_predict=True)          # the predict pass can ride in the graph as well
+    m2, s2 = t._session.predict()
+    assert np.array_equal(np.asarray(m2).ravel(), np.asarray(mg).ravel()) and np.array_equal(s2, sg)
+
+
 def test_errors_cross_the_abi_as_exceptions():
     import pymra_b200.MRATools as mt
     from pymra_b200 import _ffi

@@ -77,10 +77,16 @@ def main():
                       "wall_s": dt, "evals_per_s": count[0] / dt, "kappa_hat": float(res.x[0]),
                       "kappa_true": kappa_true, "minus2loglik": float(res.fun)}), flush=True)
 
-    # ---- frozen tree: refit on the same knots
+    # ---- frozen tree: refit on the same knots; once relaunching every kernel, once replaying the captured CUDA graph
+    for graph in ("0", "1"):
+        os.environ["PYMRA_B200_GRAPH"] = graph
+        frozen_tree(MRATree, locs, r0, cov_for, obs, R, M, kappa_true, opt, torch, graph == "1")
+
+
+def frozen_tree(MRATree, locs, r0, cov_for, obs, R, M, kappa_true, opt, torch, graph):
     np.random.seed(5)
     tree = MRATree(locs, r0, cov_for(0.5), obs, R, M=M)
-    count[0] = 0
+    count = [0]
 
     def objective2(x):
         count[0] += 1
@@ -92,7 +98,16 @@ def main():
     t0 = time.time()
     res = opt.minimize(objective2, [0.5], method="nelder-mead", options={"xatol": 1e-3, "fatol": 1e-2, "maxfev": 120})
     dt = time.time() - t0
-    print(json.dumps({"mode": "frozen tree (tree.refit per evaluation)", "evaluations": count[0], "wall_s": dt,
+    # steady state: 200 more evaluations around the optimum (the graph's one-off capture + instantiation is behind us)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    for i in range(200):
+        tree.refit(cov=cov_for(float(res.x[0]) * (1.0 + 1e-3 * (i % 7))))
+    torch.cuda.synchronize()
+    steady = 200 / (time.time() - t1)
+    print(json.dumps({"mode": "frozen tree (tree.refit per evaluation%s)" % (", one CUDA graph launch each" if graph else
+                                                                             ", kernels relaunched"),
+                      "evaluations": count[0], "wall_s": dt, "steady_state_evals_per_s": steady,
                       "evals_per_s": count[0] / dt, "kappa_hat": float(res.x[0]), "kappa_true": kappa_true,
                       "minus2loglik": float(res.fun)}), flush=True)
 

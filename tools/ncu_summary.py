@@ -29,7 +29,8 @@ COLS = [
 
 FAMILY = {"k_prior_tiles": "prior_tiles", "k_prior_groups": "prior_tiles", "k_predict_fused": "predict_fused",
           "k_assemble_A": "assemble_A", "k_leaf_solve": "leaf_solve", "k_leaf_gram": "leaf_gram",
-          "k_leaf_chol": "leaf_chol", "k_leaf_upd": "leaf_upd", "k_leaf_trsm": "leaf_trsm", "k_leaf_q": "leaf_q",
+          "k_leaf_chol": "leaf_chol", "k_leaf_upd": "leaf_upd", "k_leaf_trsm": "leaf_trsm", "k_leaf_qobs": "leaf_qobs",
+          "k_leaf_q": "leaf_q", "k_leaf_linv": "leaf_linv", "k_leaf_ut2": "leaf_ut",
           "k_fold": "fold", "k_knot_gram": "knot_gram", "k_knot_chol": "knot_chol", "k_knot_vkl": "knot_vkl",
           "k_node_chol": "node_chol", "k_node_gt": "node_gt"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
