@@ -331,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step():
         sess.likelihood_async()
-        sess.predict_dev(mean_t, sd_t, reduce=True)   # N > 1: outputs sum-reduced so every rank holds all N rows
+        sess.predict_dev(mean_t, sd_t, reduce=True)   # N > 1: the ranks' rows are gathered so every rank holds all N rows
 
     sampler = ClockSampler(local_rank) if rank == 0 else None     # polls over the warm-up and the timed steps
     for _ in range(max(args.warmup, 3)):
@@ -466,7 +466,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": args.workload, "grid": [n, n], "n_locs": N, "r0": r, "M_requested": Mreq,
                        "M_effective": M, "J": J, "cov": family, "l": l, "sig": sig, "R": R, "frac_obs": frac,
                        "nodes": int(st.n_nodes), "parallelism": ("subtree sharding at level %d over %d GPUs, one "
-                       "all-reduce of %d summary doubles per evaluation + sum-reduce of the outputs" % (
+                       "all-reduce of %d summary doubles per evaluation + all-gather of the ranks' output rows (16 B/location)" % (
                            sess.shard_level, world, 0 if sess.summary is None else sess.summary.numel()))
                        if world > 1 else "single GPU", "l2_policy": "inputs larger than L2 (basis stack %.1f GB)" % (
                            N * max(st.depth, 1) * r * 8 / 1e9),

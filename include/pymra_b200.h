@@ -160,6 +160,18 @@ int mra_run_likelihood_async(mra_handle *h, void *stream);
 int mra_run_predict_dev(mra_handle *h, void *stream, double *dev_mean, double *dev_sd);
 int mra_fetch_likelihood(mra_handle *h, void *stream, double out[2]);
 
+/* Sharded predict() without full-length zero-padded outputs (the outputs are gathered, 16 B per location).
+ * mra_predict_rows: the tree-order row ranges [start, count] this rank emits (n_ranges; ranges may be NULL to query).
+ * mra_run_predict_pack_dev: runs the downward pass (MRANode.py:486-520) for this rank's subtrees and packs its results
+ *   into dev_pack = [mean of my rows | var of my rows] (2 * n_rows doubles, rows in range order); the caller gathers
+ *   the packs of all ranks and lays them out in tree order.
+ * mra_unpermute_tree_dev: complete tree-order mean / var arrays -> caller's row order, sd = sqrt(var)
+ *   (MRANode.py:517-520, MRATree.py:90-94). */
+int mra_predict_rows(const mra_handle *h, int64_t *ranges, int32_t max_ranges, int32_t *n_ranges);
+int mra_run_predict_pack_dev(mra_handle *h, void *stream, double *dev_pack, int64_t n_rows);
+int mra_unpermute_tree_dev(mra_handle *h, void *stream, const double *dev_mean_tree, const double *dev_var_tree,
+                           double *dev_mean, double *dev_sd);
+
 /* One whole evaluation on the frozen tree as ONE CUDA graph launch (the Nelder-Mead loop of README.md:96-104
  * re-evaluates the likelihood ~100 times on the same tree): the first call captures the launches of
  * mra_run_likelihood_async (and, with_predict != 0, of mra_run_predict_dev into the handle's own result buffers), later

@@ -55,6 +55,9 @@ SIGNATURES = {
     "mra_run_likelihood_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mra_run_predict_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mra_fetch_likelihood": (C.c_int, [C.c_void_p, C.c_void_p, _pd]),
+    "mra_predict_rows": (C.c_int, [C.c_void_p, _p64, C.c_int32, _p32]),
+    "mra_run_predict_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "mra_unpermute_tree_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mra_run_graph": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "mra_set_shard": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int8)]),
     "mra_summary_size": (C.c_int, [C.c_void_p, _p64]),

@@ -5,6 +5,7 @@
 #include "../../include/pymra_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -136,8 +137,6 @@ struct mra_handle {
   std::vector<std::string> kname;
   std::vector<double> kflops, kbytes;   // algorithmic work per launch-group, accumulated at plan time
   std::vector<double> kms;
-  const char* memo_name[64] = {};   // add_work: literal pointer -> kernel id
-  int memo_id[64] = {};
   std::vector<int64_t> klaunch;
 };
 
@@ -160,6 +159,27 @@ void parallel_for(int64_t n, F fn) {
   }
   for (auto& t : th) t.join();
 }
+
+// MRA_HOST_TRACE=1: wall-clock phases of the host-side entry points on stderr (where the pre-GPU time of a construction goes)
+struct HostTrace {
+  const char* fn;
+  bool on;
+  std::chrono::steady_clock::time_point t0, last;
+  explicit HostTrace(const char* f) : fn(f), on(std::getenv("MRA_HOST_TRACE") != nullptr) {
+    t0 = last = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[host] %s: %-22s %7.3f ms\n", fn, what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  }
+  ~HostTrace() {
+    if (on)
+      fprintf(stderr, "[host] %s: total %7.3f ms\n", fn,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
 
 int fail(mra_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -265,12 +285,13 @@ size_t smem_leafq(int max_obs) {
 size_t smem_leafq2(int max_obs) {
   return sizeof(WideSmem) + sizeof(double) * ((size_t)3 * max_obs + 2 * TB + 4 * TB) + sizeof(int) * TB + 16;
 }
-size_t smem_gram() { return GS1 + sizeof(int) * 2 * TB; }
+size_t smem_gram() { return GS1 + sizeof(double) * 4 * TB + sizeof(int) * 2 * TB; }
 size_t smem_solve() { return GS1; }
 size_t smem_plain() { return sizeof(GemmSmemT<4>); }   // k_assemble_A: up to 4 children per product
-size_t smem_predict(int r) {
+size_t smem_predict(int r, int depth) {
   int ldT = ((r + 15) / 16) * 16 + 4;
-  return GS + sizeof(double) * ((size_t)(r > TB ? TB * ldT : 0) + 2 * TB) + sizeof(int) * MAX_LEVELS;
+  return GS + sizeof(double) * ((size_t)(r > TB ? TB * ldT : 0) + 2 * TB + (size_t)std::max(depth, 1) * r) +
+         sizeof(int) * MAX_LEVELS + sizeof(long long) * 2 * MAX_LEVELS;
 }
 
 // Kernels are instantiated for VEC = 2 (16-byte cp.async, even r) and VEC = 1 (odd r).
@@ -325,7 +346,7 @@ cudaError_t smem_at_least(K kernel, size_t bytes) {
   } while (0)
 
 template <int V_, int J_>
-cudaError_t configure_vec_nj(int r) {
+cudaError_t configure_vec_nj(int r, int depth) {
   cudaError_t e;
 #define SET_(k, bytes)              \
   e = smem_at_least(k, (bytes));    \
@@ -336,7 +357,7 @@ cudaError_t configure_vec_nj(int r) {
     SET_((k_prior_groups<J_>), smem_pgroups(r));
   }
   SET_((k_node_gt<V_, J_>), GS1);
-  SET_((k_predict_fused<V_, J_>), smem_predict(r));
+  SET_((k_predict_fused<V_, J_>), smem_predict(r, depth));
 #undef SET_
   return cudaSuccess;
 }
@@ -358,14 +379,14 @@ cudaError_t configure_vec(int r, int max_obs) {
   SET_(k_leaf_solve_qt<V_>, smem_solve());
   SET_(k_assemble_A<V_>, smem_plain());
 
-  SET_(k_fold<V_>, GS1);
+  SET_(k_fold<V_>, GS1 + sizeof(long long) * MAX_LEVELS);
 #undef SET_
   return cudaSuccess;
 }
 
 int configure_kernels(mra_handle* h) {
   MRA_FOR_VEC(h, CU(configure_vec<V_>(h->r, h->max_leaf_obs)));
-  MRA_FOR_VEC_NJ(h, CU((configure_vec_nj<V_, J_>(h->r))));
+  MRA_FOR_VEC_NJ(h, CU((configure_vec_nj<V_, J_>(h->r, h->depth))));
   CU(smem_at_least(k_knot_chol, smem_cholinv(h->r)));
   CU(smem_at_least(k_node_chol, smem_cholinv(h->r)));
   CU(smem_at_least(k_leaf_chol, smem_cholinv(TB)));
@@ -386,16 +407,7 @@ int kid(mra_handle* h, const std::string& name) {
   return id;
 }
 
-void add_work(mra_handle* h, const char* name, double flops, double bytes) {
-  // called ~10x per node from mra_plan: memoise the id per literal (pointer identity) instead of a map lookup
-  int id = -1;
-  const unsigned slot = (unsigned)((reinterpret_cast<uintptr_t>(name) >> 2) & 63);
-  if (h->memo_name[slot] == name) id = h->memo_id[slot];
-  if (id < 0) {
-    id = kid(h, name);
-    h->memo_name[slot] = name;
-    h->memo_id[slot] = id;
-  }
+inline void add_w(mra_handle* h, int id, double flops, double bytes) {
   h->kflops[id] += flops;
   h->kbytes[id] += bytes;
 }
@@ -524,8 +536,8 @@ int leaf_terms(mra_handle* h, cudaStream_t st, const DevCtx& c, Range rg) {
   if (h->leaf_v2) {
     MRA_FOR_VEC(h, LAUNCH("leaf_linv", k_leaf_linv<V_><<<nleaf, NT, GS1, st>>>(c, leaf_list)));
     if (h->max_leaf_W > 1)
-      MRA_FOR_VEC(h, LAUNCH("leaf_ut", k_leaf_ut2<V_><<<(unsigned)nleaf * nbo * nt3, NT, smem_ut2(h->max_leaf_obs), st>>>(
-                                           c, leaf_list, nbo * nt3, nt3)));
+      MRA_FOR_VEC(h, LAUNCH("leaf_ut", k_leaf_ut2<V_><<<(unsigned)nleaf * nbo, NT, smem_ut2(h->max_leaf_obs), st>>>(
+                                           c, leaf_list, nbo, nt3)));
   } else {
     MRA_FOR_VEC(h, LAUNCH("leaf_solve", k_leaf_solve_ut<V_><<<(unsigned)nleaf * nt3, NT, smem_solve(), st>>>(c, leaf_list, nt3)));
   }
@@ -658,11 +670,11 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
       h->leafq_done = true;
     }
     if (!h->fold_items.empty())
-      MRA_FOR_VEC(h, LAUNCH("fold", k_fold<V_><<<(unsigned)h->fold_items.size(), NT, GS1, st>>>(
+      MRA_FOR_VEC(h, LAUNCH("fold", k_fold<V_><<<(unsigned)h->fold_items.size(), NT, GS1 + sizeof(long long) * MAX_LEVELS, st>>>(
                                         c, at<int4>(h, L.fold))));
     if (!h->leaf_tiles.empty())
-      MRA_FOR_VEC_NJ(h, LAUNCH("predict_fused", k_predict_fused<V_, J_><<<(unsigned)h->leaf_tiles.size(), NT, smem_predict(r), st>>>(
-                                                 c, at<int4>(h, L.ltiles))));
+      MRA_FOR_VEC_NJ(h, LAUNCH("predict_fused", k_predict_fused<V_, J_><<<(unsigned)h->leaf_tiles.size(), NT, smem_predict(r, h->depth), st>>>(
+                                                 c, at<int4>(h, L.ltiles), h->depth)));
     h->pred_done = true;   // V now holds the posterior-updated basis; results stay cached in mean/var
   }
   double* om = dev_mean ? dev_mean : at<double>(h, L.out_mean);
@@ -710,12 +722,24 @@ void build_lists(mra_handle* h) {
   };
   if (s == 0) {
     for (int n = 0; n < nn; ++n) {
-      if (h->kind[n] == KIND_INTERNAL) {
-        h->internal_at[h->level[n]].push_back(n);
-        add_tiles(n, h->row_start[n], h->row_count[n]);
-      } else {
-        h->leaves.push_back(n);
+      if (h->kind[n] == KIND_INTERNAL) h->internal_at[h->level[n]].push_back(n);
+      else h->leaves.push_back(n);
+    }
+    {
+      // the tile lists of the levels are independent of each other: one host thread per level (N / 64 tiles each)
+      std::vector<std::thread> th;
+      for (size_t m = 0; m < nlev; ++m) {
+        if (h->internal_at[m].empty()) continue;
+        th.emplace_back([h, m] {
+          std::vector<int4>& tl = h->ptiles_at[m];
+          for (int n : h->internal_at[m]) {
+            const int64_t row0 = h->row_start[n], cnt = h->row_count[n];
+            for (int64_t r0 = 0; r0 < cnt; r0 += TB)
+              tl.push_back(make_int4(n, (int)(row0 + r0), (int)std::min<int64_t>(TB, cnt - r0), 0));
+          }
+        });
       }
+      for (auto& t : th) t.join();
     }
     add_emit(0, h->N);
     h->n_regular_tiles.assign(nlev, 0);
@@ -761,7 +785,8 @@ void build_lists(mra_handle* h) {
   // groups of the regular prior tiles: consecutive full tiles of one node, at most PG per group
   h->pgroups_at.assign(h->ptiles_at.size(), {});
   h->group_of_tile.assign(h->ptiles_at.size(), {});
-  for (size_t m = 0; m < h->ptiles_at.size(); ++m) {
+  std::vector<std::thread> gth;
+  for (size_t m = 0; m < h->ptiles_at.size(); ++m) gth.emplace_back([h, m] {
     const std::vector<int4>& tl = h->ptiles_at[m];
     std::vector<int4>& gl = h->pgroups_at[m];
     std::vector<int>& got = h->group_of_tile[m];
@@ -779,7 +804,8 @@ void build_lists(mra_handle* h) {
       else gl.push_back(make_int4(t.x, t.y, t.z, 0));
       got[i] = (int)gl.size() - 1;
     }
-  }
+  });
+  for (auto& t : gth) t.join();
   h->leaf_tiles.clear();
   for (int n : h->leaves)
     for (int64_t r0 = 0; r0 < h->row_count[n]; r0 += TB)
@@ -927,6 +953,7 @@ int mra_set_structure(mra_handle* h, const mra_structure* s) {
   if (s->r < 1 || s->r > 128) return fail(h, MRA_ERR_ARG, "r must be in [1, 128] in this build");
   if (s->n_nodes < 1 || s->depth < 0) return fail(h, MRA_ERR_ARG, "empty tree");
   if (s->depth >= MAX_LEVELS) return fail(h, MRA_ERR_ARG, "tree deeper than MAX_LEVELS in this build");
+  HostTrace tr("set_structure");
   h->N = s->n_locs;
   h->dim = s->dim;
   h->r = s->r;
@@ -943,10 +970,21 @@ int mra_set_structure(mra_handle* h, const mra_structure* s) {
   h->knot_off.assign(s->node_knot_off, s->node_knot_off + nn);
   h->level_off.assign(s->level_off, s->level_off + s->depth + 2);
   h->knot_rows.resize(s->n_knot_rows);
-  for (int64_t i = 0; i < s->n_knot_rows; ++i) {
-    if (s->knot_rows[i] < 0 || s->knot_rows[i] >= h->N) return fail(h, MRA_ERR_ARG, "knot row out of range");
-    h->knot_rows[i] = (int)s->knot_rows[i];
+  {
+    std::vector<int> bad(1, 0);
+    int* badp = bad.data();
+    int* dst = h->knot_rows.data();
+    const int64_t* src = s->knot_rows;
+    const int64_t N = h->N;
+    parallel_for(s->n_knot_rows, [=](int64_t a, int64_t b) {
+      for (int64_t i = a; i < b; ++i) {
+        if (src[i] < 0 || src[i] >= N) *badp = 1;
+        dst[i] = (int)src[i];
+      }
+    });
+    if (bad[0]) return fail(h, MRA_ERR_ARG, "knot row out of range");
   }
+  tr.mark("node arrays + knots");
   h->perm.resize(h->N);
   {
     std::vector<int> bad(1, 0);
@@ -972,11 +1010,14 @@ int mra_set_structure(mra_handle* h, const mra_structure* s) {
       if (h->knot_off[n] < 0 || h->knot_off[n] + h->r > s->n_knot_rows)
         return fail(h, MRA_ERR_ARG, "internal node without r knots");
       if (h->child_count[n] <= 0) return fail(h, MRA_ERR_ARG, "internal node without children");
+      if (h->child_count[n] > 16) return fail(h, MRA_ERR_ARG, "more than 16 children per node (the reference's IDs allow 9)");
     }
   }
+  tr.mark("perm + validation");
   h->shard_level = 0;
   h->role.assign(nn, 1);
   build_lists(h);
+  tr.mark("build_lists");
   h->ldv = std::max<long long>(2, ((long long)std::max(h->depth, 1) * h->r + 1) / 2 * 2);
   h->has_structure = true;
   h->planned = h->bound = h->uploaded = h->lik_done = h->pred_done = false;
@@ -986,6 +1027,7 @@ int mra_set_structure(mra_handle* h, const mra_structure* s) {
 int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspace_bytes) {
   if (!h || !obs || !workspace_bytes) return MRA_ERR_ARG;
   if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
+  HostTrace tr("plan");
   const int nn = h->n_nodes, r = h->r;
   h->want_predict = want_predict != 0;
   drop_graph(h);
@@ -994,16 +1036,46 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
             linv_off = 0, utt_off = 0;
   h->max_leaf_obs = h->max_leaf_rows = h->max_leaf_unobs = 0;
   h->max_leaf_W = 1;
+  // kernel-family ids of the work accounting, resolved once (the node loop below makes ~15 updates per node)
+  const int W_assemble_A = kid(h, "assemble_A");
+  const int W_fold = kid(h, "fold");
+  const int W_knot_chol = kid(h, "knot_chol");
+  const int W_knot_gram = kid(h, "knot_gram");
+  const int W_knot_vkl = kid(h, "knot_vkl");
+  const int W_leaf_chol = kid(h, "leaf_chol");
+  const int W_leaf_gram = kid(h, "leaf_gram");
+  const int W_leaf_gram_T = kid(h, "leaf_gram_T");
+  const int W_leaf_linv = kid(h, "leaf_linv");
+  const int W_leaf_q = kid(h, "leaf_q");
+  const int W_leaf_qobs = kid(h, "leaf_qobs");
+  const int W_leaf_solve = kid(h, "leaf_solve");
+  const int W_leaf_solve_Q = kid(h, "leaf_solve_Q");
+  const int W_leaf_trsm = kid(h, "leaf_trsm");
+  const int W_leaf_upd = kid(h, "leaf_upd");
+  const int W_leaf_ut = kid(h, "leaf_ut");
+  const int W_node_chol = kid(h, "node_chol");
+  const int W_node_gt = kid(h, "node_gt");
+  const int W_predict_fused = kid(h, "predict_fused");
+  const int W_prior_tiles = kid(h, "prior_tiles");
+  const int W_unpermute = kid(h, "unpermute");
   for (auto& f : h->kflops) f = 0.0;
   for (auto& f : h->kbytes) f = 0.0;
   std::vector<uint8_t, NoInit<uint8_t>> finite_row((size_t)h->N);     // np.isfinite(obs) in tree order (MRANode.py:415)
   {
+    // two passes: the flags in the caller's order (a sequential scan of obs), then a gather of BYTES through the
+    // permutation -- the random reads hit a 1-byte-per-location table that stays in cache, not the 8-byte observations
+    std::vector<uint8_t, NoInit<uint8_t>> finite_c((size_t)h->N);
+    uint8_t* fc = finite_c.data();
+    parallel_for(h->N, [=](int64_t a, int64_t b) {
+      for (int64_t i = a; i < b; ++i) fc[i] = std::isfinite(obs[i]) ? 1 : 0;
+    });
     uint8_t* fr = finite_row.data();
     const int* pm = h->perm.data();
     parallel_for(h->N, [=](int64_t a, int64_t b) {
-      for (int64_t i = a; i < b; ++i) fr[i] = std::isfinite(obs[pm[i]]) ? 1 : 0;
+      for (int64_t i = a; i < b; ++i) fr[i] = fc[pm[i]];
     });
   }
+  tr.mark("finite flags");
   // observed / unobserved row lists of every leaf of this rank: count per leaf, prefix, fill -- all in parallel
   std::vector<int> leaf_ids, leaf_obs_off, leaf_unobs_off;
   for (int n = 0; n < nn; ++n)
@@ -1069,6 +1141,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       }
     });
   }
+  tr.mark("leaf row lists");
   std::vector<double> my_rows_prior((size_t)nn, 0.0), my_rows_pred((size_t)nn, 0.0);
   for (size_t m = 0; m < h->ptiles_at.size(); ++m)
     for (size_t i = 0; i < h->ptiles_at[m].size(); ++i) {
@@ -1107,17 +1180,17 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       // sharded handle, whose tile list holds only this rank's pieces (+ gathered knot rows, prior pass only)
       const double nr = my_rows_prior[n], nrp = my_rows_pred[n], rr = (double)r;
       const double Waf = Kv + rr + 1;
-      add_work(h, "knot_gram", rr * rr * Kv, 8.0 * (2.0 * rr * Kv + rr * rr / 2));
-      add_work(h, "knot_chol", 2.0 * rr * rr * rr / 3.0, 8.0 * rr * rr);
-      add_work(h, "knot_vkl", 2.0 * rr * rr * Kv, 8.0 * (2.0 * rr * Kv + rr * rr));
-      add_work(h, "prior_tiles", 2.0 * nr * rr * Kv + nr * rr * rr, 8.0 * nr * (Kv + rr + 2));
+      add_w(h, W_knot_gram, rr * rr * Kv, 8.0 * (2.0 * rr * Kv + rr * rr / 2));
+      add_w(h, W_knot_chol, 2.0 * rr * rr * rr / 3.0, 8.0 * rr * rr);
+      add_w(h, W_knot_vkl, 2.0 * rr * rr * Kv, 8.0 * (2.0 * rr * Kv + rr * rr));
+      add_w(h, W_prior_tiles, 2.0 * nr * rr * Kv + nr * rr * rr, 8.0 * nr * (Kv + rr + 2));
       double fa = 0;     // assemble: symmetric half of W x W, K = n_obs (leaf child) or r (internal child)
       for (int ch = d.child_start; ch < d.child_start + d.child_count; ++ch)
         if (h->kind[ch] == KIND_INTERNAL && !(h->shard_level > 0 && d.level == h->shard_level - 1)) fa += Waf * Waf * rr;
-      add_work(h, "assemble_A", fa, 8.0 * Waf * Waf);
-      add_work(h, "node_chol", 2.0 * rr * rr * rr / 3.0, 8.0 * 2.0 * rr * rr);
-      add_work(h, "node_gt", (Kv + 1) * rr * rr, 8.0 * (rr * rr + 2 * (Kv + 1) * rr));
-      add_work(h, "predict_fused", nrp * rr * rr + 2.0 * nrp * rr * Kv + 4.0 * nrp * rr, 8.0 * nrp * rr);
+      add_w(h, W_assemble_A, fa, 8.0 * Waf * Waf);
+      add_w(h, W_node_chol, 2.0 * rr * rr * rr / 3.0, 8.0 * 2.0 * rr * rr);
+      add_w(h, W_node_gt, (Kv + 1) * rr * rr, 8.0 * (rr * rr + 2 * (Kv + 1) * rr));
+      add_w(h, W_predict_fused, nrp * rr * rr + 2.0 * nrp * rr * Kv + 4.0 * nrp * rr, 8.0 * nrp * rr);
     } else {
       if (d.kind == KIND_LEAF) {
         d.obs_off = leaf_obs_off[leaf_cursor];
@@ -1146,38 +1219,39 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       h->max_leaf_rows = std::max(h->max_leaf_rows, d.row_count);
       if (d.n_obs > 0) h->max_leaf_W = std::max(h->max_leaf_W, d.W);
       const double no = d.n_obs, nl = d.row_count, W = Kv + 1;
-      add_work(h, "leaf_gram", no * no * Kv, 8.0 * (no * Kv + no * no / 2));
+      add_w(h, W_leaf_gram, no * no * Kv, 8.0 * (no * Kv + no * no / 2));
       for (int pb = 0; pb * TB < d.n_obs; ++pb) {      // blocked factorisation as executed (triangular halves)
         const double nv = std::min(TB, d.n_obs - pb * TB), Kp = (double)pb * TB, below = no - Kp - nv;
-        add_work(h, "leaf_chol", 2.0 * nv * nv * nv / 3.0, 8.0 * 2.0 * nv * nv);
-        if (pb > 0) add_work(h, "leaf_upd", nv * nv * Kp, 8.0 * (nv * Kp + nv * nv));
-        if (below > 0) add_work(h, "leaf_trsm", below * nv * (2.0 * Kp + nv), 8.0 * (below * (Kp + 2 * nv) + nv * Kp + nv * nv));
+        add_w(h, W_leaf_chol, 2.0 * nv * nv * nv / 3.0, 8.0 * 2.0 * nv * nv);
+        if (pb > 0) add_w(h, W_leaf_upd, nv * nv * Kp, 8.0 * (nv * Kp + nv * nv));
+        if (below > 0) add_w(h, W_leaf_trsm, below * nv * (2.0 * Kp + nv), 8.0 * (below * (Kp + 2 * nv) + nv * Kp + nv * nv));
       }
       if (h->leaf_v2) {
         for (int bj = 0; (bj + 1) * TB < d.n_obs; ++bj)
           for (int bi = bj + 1; bi * TB < d.n_obs; ++bi) {
             const double nvi = std::min(TB, d.n_obs - bi * TB);
-            add_work(h, "leaf_linv", nvi * TB * TB * (bi - bj) + nvi * nvi * TB, 8.0 * (3.0 * nvi * TB + TB * TB * (bi - bj)));
+            add_w(h, W_leaf_linv, nvi * TB * TB * (bi - bj) + nvi * nvi * TB, 8.0 * (3.0 * nvi * TB + TB * TB * (bi - bj)));
           }
-        add_work(h, "leaf_linv", 0.0, 8.0 * no * no);
-        add_work(h, "leaf_ut", no * no * Kv, 8.0 * (3 * no * Kv + no * no / 2));
+        add_w(h, W_leaf_linv, 0.0, 8.0 * no * no);
+        add_w(h, W_leaf_ut, no * no * Kv, 8.0 * (3 * no * Kv + no * no / 2));
       } else {
-        add_work(h, "leaf_solve", no * no * W, 8.0 * (2 * no * W + no * no / 2));
+        add_w(h, W_leaf_solve, no * no * W, 8.0 * (2 * no * W + no * no / 2));
       }
-      add_work(h, "assemble_A", W * W * no, 8.0 * no * W);
+      add_w(h, W_assemble_A, W * W * no, 8.0 * no * W);
       if (d.kind == KIND_LEAF) {
-        add_work(h, "predict_fused", 2.0 * nl * Kv, 8.0 * nl * (Kv + 2));
+        add_w(h, W_predict_fused, 2.0 * nl * Kv, 8.0 * nl * (Kv + 2));
         if (h->leaf_v2) {
-          add_work(h, "leaf_q", 2.0 * (nl - no) * no * Kv + (nl - no) * no * no, 8.0 * ((nl - no) * (Kv + no) + no * (Kv + no / 2)));
-          add_work(h, "leaf_qobs", 0.0, 8.0 * 2.0 * no * no);
+          add_w(h, W_leaf_q, 2.0 * (nl - no) * no * Kv + (nl - no) * no * no, 8.0 * ((nl - no) * (Kv + no) + no * (Kv + no / 2)));
+          add_w(h, W_leaf_qobs, 0.0, 8.0 * 2.0 * no * no);
         } else {
-          add_work(h, "leaf_gram_T", 2.0 * (nl - no) * no * Kv, 8.0 * ((nl + no) * Kv + nl * no));
-          add_work(h, "leaf_solve_Q", nl * no * no, 8.0 * (2 * nl * no + no * no / 2));
+          add_w(h, W_leaf_gram_T, 2.0 * (nl - no) * no * Kv, 8.0 * ((nl + no) * Kv + nl * no));
+          add_w(h, W_leaf_solve_Q, nl * no * no, 8.0 * (2 * nl * no + no * no / 2));
         }
-        add_work(h, "predict_fused", 2.0 * nl * no * W + 2.0 * nl * no, 8.0 * (nl * no + no * W));
+        add_w(h, W_predict_fused, 2.0 * nl * no * W + 2.0 * nl * no, 8.0 * (nl * no + no * W));
       }
     }
   }
+  tr.mark("node loop");
   h->n_obs_total = (int64_t)h->obs_rows.size();
   h->fold_items.clear();
   if (h->want_predict) {
@@ -1190,14 +1264,13 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       if (d.kind == KIND_INTERNAL) nxt = nct;
       else if (d.kind == KIND_LEAF && d.n_obs > 0) nxt = (d.n_obs + TB - 1) / TB;
       else continue;
-      for (int j = 0; j < d.level; ++j)
-        for (int ct = 0; ct < nct; ++ct)
-          for (int xt = 0; xt < nxt; ++xt) h->fold_items.push_back(make_int4(n, j, ct, xt));
+      for (int ct = 0; ct < nct; ++ct)
+        for (int xt = 0; xt < nxt; ++xt) h->fold_items.push_back(make_int4(n, 0, ct, xt));      // the CTA walks the levels j
       const double cols = d.kind == KIND_INTERNAL ? r : d.n_obs;
-      add_work(h, "fold", 2.0 * d.level * (double)r * r * cols, 8.0 * 2.0 * d.level * r * cols);
+      add_w(h, W_fold, 2.0 * d.level * (double)r * r * cols, 8.0 * 2.0 * d.level * r * cols);
     }
   }
-  add_work(h, "unpermute", 0.0, 8.0 * 4.0 * (double)h->N);
+  add_w(h, W_unpermute, 0.0, 8.0 * 4.0 * (double)h->N);
   h->flops_lik = h->flops_pred = 0.0;
   for (size_t i = 0; i < h->kname.size(); ++i) {
     const std::string& nm = h->kname[i];
@@ -1205,6 +1278,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
                       nm == "predict_fused" || nm == "unpermute";
     (pred ? h->flops_pred : h->flops_lik) += h->kflops[i];
   }
+  tr.mark("fold items");
   // ---- arena layout
   Arena ar;
   Layout& L = h->lay;
@@ -1314,9 +1388,14 @@ static int upload_impl(mra_handle* h, const double* locs, const double* obs, con
     if (!h->internal_at[m].empty())
       CU(cudaMemcpyAsync(h->ws + L.lists + h->list_off[m], h->internal_at[m].data(),
                          sizeof(int) * h->internal_at[m].size(), cudaMemcpyHostToDevice, st));
-    if (!h->ptiles_at[m].empty())
-      CU(cudaMemcpyAsync(h->ws + L.ptiles + h->ptiles_off[m], h->ptiles_at[m].data(),
-                         sizeof(int4) * h->ptiles_at[m].size(), cudaMemcpyHostToDevice, st));
+    {
+      // regular tiles run through the group list when it is in use: only the gathered tiles are needed on the device
+      const bool grouped = h->use_groups && (h->r & 1) == 0;
+      const size_t first = grouped ? (size_t)h->n_regular_tiles[m] : 0, cnt = h->ptiles_at[m].size() - first;
+      if (cnt > 0)
+        CU(cudaMemcpyAsync(h->ws + L.ptiles + h->ptiles_off[m] + sizeof(int4) * first, h->ptiles_at[m].data() + first,
+                           sizeof(int4) * cnt, cudaMemcpyHostToDevice, st));
+    }
     if (!h->pgroups_at[m].empty())
       CU(cudaMemcpyAsync(h->ws + L.pgroups + h->pgroups_off[m], h->pgroups_at[m].data(),
                          sizeof(int4) * h->pgroups_at[m].size(), cudaMemcpyHostToDevice, st));
@@ -1703,6 +1782,89 @@ int mra_run_predict_dev(mra_handle* h, void* stream, double* dev_mean, double* d
   if (!h->want_predict) return fail(h, MRA_ERR_STATE, "mra_plan was called with want_predict = 0");
   DEVICE_SCOPE(h);
   return launch_predict(h, static_cast<cudaStream_t>(stream), dev_mean, dev_sd);
+}
+
+// Sharded predict without zero-padded full-length outputs ("gather 16 B / location"): the tree-order row
+// ranges this rank emits, its results packed contiguously ([mean of all my rows | var of all my rows]), and the
+// un-permutation of complete tree-order arrays on whichever rank has gathered them.
+int mra_predict_rows(const mra_handle* h, int64_t* ranges, int32_t max_ranges, int32_t* n_ranges) {
+  if (!h || !n_ranges) return MRA_ERR_ARG;
+  int n = 0;
+  int64_t s0 = -1, e0 = -1;
+  auto flush = [&]() {
+    if (s0 < 0) return;
+    if (ranges && n < max_ranges) {
+      ranges[2 * n] = s0;
+      ranges[2 * n + 1] = e0 - s0;
+    }
+    ++n;
+  };
+  for (const int2& ch : h->emit_chunks) {
+    if (s0 >= 0 && ch.x == e0) {
+      e0 += ch.y;
+      continue;
+    }
+    flush();
+    s0 = ch.x;
+    e0 = (int64_t)ch.x + ch.y;
+  }
+  flush();
+  *n_ranges = n;
+  return (ranges && n > max_ranges) ? MRA_ERR_NOMEM : MRA_OK;
+}
+
+int mra_run_predict_pack_dev(mra_handle* h, void* stream, double* dev_pack, int64_t n_rows) {
+  if (!h || !dev_pack) return MRA_ERR_ARG;
+  if (!h->lik_done) return fail(h, MRA_ERR_STATE, "mra_run_likelihood must be called first");
+  if (!h->want_predict) return fail(h, MRA_ERR_STATE, "mra_plan was called with want_predict = 0");
+  DEVICE_SCOPE(h);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t mine = 0;
+  for (const int2& ch : h->emit_chunks) mine += ch.y;
+  if (mine != n_rows) return fail(h, MRA_ERR_ARG, "n_rows is not the number of rows this rank emits");
+  // the predict kernels proper (no un-permutation: emit list left out)
+  {
+    std::vector<int2> none;
+    none.swap(h->emit_chunks);
+    int rc = launch_predict(h, st, at<double>(h, h->lay.out_mean), at<double>(h, h->lay.out_sd));
+    none.swap(h->emit_chunks);
+    if (rc) return rc;
+  }
+  int64_t off = 0, s0 = -1, e0 = -1;
+  const double* mean = at<double>(h, h->lay.mean);
+  const double* var = at<double>(h, h->lay.var);
+  auto flush = [&]() -> cudaError_t {
+    if (s0 < 0) return cudaSuccess;
+    cudaError_t e = cudaMemcpyAsync(dev_pack + off, mean + s0, sizeof(double) * (e0 - s0), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(dev_pack + n_rows + off, var + s0, sizeof(double) * (e0 - s0), cudaMemcpyDeviceToDevice, st);
+    off += e0 - s0;
+    return e;
+  };
+  for (const int2& ch : h->emit_chunks) {
+    if (s0 >= 0 && ch.x == e0) {
+      e0 += ch.y;
+      continue;
+    }
+    CU(flush());
+    s0 = ch.x;
+    e0 = (int64_t)ch.x + ch.y;
+  }
+  CU(flush());
+  return MRA_OK;
+}
+
+int mra_unpermute_tree_dev(mra_handle* h, void* stream, const double* dev_mean_tree, const double* dev_var_tree,
+                           double* dev_mean, double* dev_sd) {
+  if (!h || !dev_mean_tree || !dev_var_tree || !dev_mean || !dev_sd) return MRA_ERR_ARG;
+  if (!h->uploaded) return fail(h, MRA_ERR_STATE, "mra_upload_data must be called first");
+  DEVICE_SCOPE(h);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DevCtx c = make_ctx(h);
+  k_unpermute_all<<<(unsigned)((h->N + 255) / 256), 256, 0, st>>>(dev_mean_tree, dev_var_tree, at<int>(h, h->lay.perm),
+                                                                  (int)h->N, dev_mean, dev_sd, c.P, c.status);
+  CU(cudaGetLastError());
+  return MRA_OK;
 }
 
 int mra_run_predict(mra_handle* h, void* stream, double* mean, double* sd) {

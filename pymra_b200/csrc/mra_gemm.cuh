@@ -129,10 +129,11 @@ __device__ __forceinline__ void stage_load(double* st, const double* const* rows
 // k index kk (0..15) inside the chunk.
 // mrows: valid rows of the output tile; warps whose 16 rows lie outside are skipped (their accumulators
 // keep their value, zero if the tile was zeroed).  Column-group predication was measured slower (r01g).
-// jlo: column groups j < jlo are skipped (their B rows are known to be zero over this chunk: the operand is a
-// lower-triangular factor, whose row n is zero beyond k = n); 0 = all groups.
+// (Skipping the all-zero column groups of a triangular B operand with a per-group predicate was measured SLOWER, twice:
+// r01g for ragged column counts, r04e for the Linv / Lp^-1 operands -- predict_fused 43.7 -> 50.3 ms.  The unrolled,
+// unpredicated DMMA stream is worth more than the 37 % of the flops such a segment could save.)
 template <int NJ, class GA, class GB>
-__device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows = TB, int ncols = TB, int jlo = 0) {
+__device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows = TB, int ncols = TB) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp * 16;
   if (wm >= mrows) return;
@@ -144,13 +145,11 @@ __device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows
 #pragma unroll
     for (int i = 0; i < 2; ++i) a[i] = ga(wm + i * 8 + g, ks + q);
 #pragma unroll
-    for (int j = 0; j < NJ; ++j)
-      if (j >= jlo) b[j] = gb(j * 8 + g, ks + q);
+    for (int j = 0; j < NJ; ++j) b[j] = gb(j * 8 + g, ks + q);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < NJ; ++j)
-        if (j >= jlo) dmma884(acc.v[i][j], a[i], b[j]);
+      for (int j = 0; j < NJ; ++j) dmma884(acc.v[i][j], a[i], b[j]);
   }
 }
 
@@ -226,12 +225,9 @@ struct NoGen {
   __device__ double operator()(int, int) const { return 0.0; }
 };
 
-// tri0_col0 >= 0: segment 0's B operand is a lower-triangular factor whose row rr is column tri0_col0 + rr of the
-// factor (zero beyond k = tri0_col0 + rr); the all-zero column groups of every chunk of that segment are skipped.
 template <int VEC, bool GEN = false, bool CACHE_PTRS = true, int NJ, class FA, class FB, class FK, class SM, class FG = NoGen>
 __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB fb, FK fk, SM& sm,
-                                              const double* dummy, int mrows = TB, int ncols = TB, FG fg = FG(),
-                                              int tri0_col0 = -1) {
+                                              const double* dummy, int mrows = TB, int ncols = TB, FG fg = FG()) {
   constexpr int BR = 8 * NJ;            // rows of the B operand that exist
   constexpr int BI = (BR + 15) / 16;    // 16-row groups of B a thread copies (16-byte path)
   __syncthreads();
@@ -247,7 +243,6 @@ __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB
   __syncthreads();
   int nk = 0;
   for (int s = 0; s < nseg; ++s) nk += (sm.seg_k[s] + KC - 1) / KC;
-  const int nk0 = (sm.seg_k[0] + KC - 1) / KC;
   // loader cursor; with 16-byte copies the four row pointers per operand of the current segment are kept in
   // registers (re-read from the tables only when the segment changes)
   int lseg = 0, lk0 = 0, cached = -1;
@@ -321,10 +316,8 @@ __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB
     }
     const double* sa = sm.a[buf];
     const double* sb = sm.b[buf];
-    int jlo = 0;
-    if (tri0_col0 >= 0 && kt < nk0) jlo = max(0, (kt * KC - tri0_col0) >> 3);      // groups with 8 j + 7 + col0 < 16 kt
     chunk_mma(acc, [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; },
-              [&](int row, int kk) -> double { return sb[stage_pos(row, kk)]; }, mrows, ncols, jlo);
+              [&](int row, int kk) -> double { return sb[stage_pos(row, kk)]; }, mrows, ncols);
     if (++buf == NSTAGE) buf = 0;
   }
   cp_async_wait<0>();
@@ -393,11 +386,11 @@ __device__ __forceinline__ void tile_gemm_kmajorB(AccT<NJ>& acc, int K, FA fa, c
   cp_async_wait<0>();
 }
 
-// As tile_gemm_kmajorB, but B's K rows are gathered: rowk[k] -> start of B's row k (columns n0 .. of that row are
-// rowk[k] + n), nullptr = zero row.  rowk lives in shared memory and holds at least K entries.
+// As tile_gemm_kmajorB, but B's K rows are gathered: rowk[k] -> start of B's row k (column n of the tile is
+// rowk[k][col0 + n]), nullptr = zero row.  rowk lives in shared memory and holds at least K entries.
 template <int VEC, int NJ, class FA, class SM>
 __device__ __forceinline__ void tile_gemm_kmajorB_rows(AccT<NJ>& acc, int K, FA fa, const double* const* rowk, int ncols,
-                                                       SM& sm, const double* dummy) {
+                                                       SM& sm, const double* dummy, int col0 = 0) {
   __syncthreads();
   if (threadIdx.x < TB) sm.row_a[0][threadIdx.x] = fa((int)threadIdx.x);
   __syncthreads();
@@ -409,7 +402,7 @@ __device__ __forceinline__ void tile_gemm_kmajorB_rows(AccT<NJ>& acc, int K, FA 
         const int kr = cch >> 5, n0 = (cch & 31) * 2, k = k0 + kr;
         const double* p = k < K ? rowk[k] : nullptr;
         const int nv = p ? min(max(ncols - n0, 0), 2) * 8 : 0;
-        cp_async_16(st + kstage_pos(kr, n0), nv ? p + n0 : dummy, nv);
+        cp_async_16(st + kstage_pos(kr, n0), nv ? p + col0 + n0 : dummy, nv);
       }
     } else {
 #pragma unroll
@@ -418,7 +411,7 @@ __device__ __forceinline__ void tile_gemm_kmajorB_rows(AccT<NJ>& acc, int K, FA 
         const int kr = cch >> 6, n = cch & 63, k = k0 + kr;
         const double* p = k < K ? rowk[k] : nullptr;
         const int nv = (p && n < ncols) ? 8 : 0;
-        cp_async_8(st + kstage_pos(kr, n), nv ? p + n : dummy, nv);
+        cp_async_8(st + kstage_pos(kr, n), nv ? p + col0 + n : dummy, nv);
       }
     }
   };

@@ -214,20 +214,78 @@ class DeviceSession(object):
         self.check(st)
         return float(out[0]), float(out[1])
 
+    # ---- sharded predict: every rank packs the rows it owns, the packs are gathered (16 B per location in total)
+    def my_rows(self):
+        """Tree-order row ranges [(start, count), ..] whose predictions this rank emits."""
+        n = C.c_int32()
+        self.check(self.lib.mra_predict_rows(self.h, None, 0, C.byref(n)))
+        buf = np.zeros(2 * max(1, n.value), dtype=np.int64)
+        self.check(self.lib.mra_predict_rows(self.h, buf.ctypes.data_as(C.POINTER(C.c_int64)), n.value, C.byref(n)))
+        return [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(n.value)]
+
+    def _gather_layout(self):
+        """(ranges of every rank, rows per rank, padded pack length) -- exchanged once per session."""
+        if getattr(self, "_layout", None) is None:
+            import torch
+            import torch.distributed as dist
+            mine = self.my_rows()
+            k = torch.tensor([len(mine)], dtype=torch.int64, device=self.dev)
+            ks = [torch.zeros_like(k) for _ in range(self.world)]
+            dist.all_gather(ks, k, group=self.group)
+            kmax = max(int(x.item()) for x in ks)
+            flat = torch.zeros(2 * max(1, kmax), dtype=torch.int64, device=self.dev)
+            if mine:
+                flat[:2 * len(mine)] = torch.tensor([v for rg in mine for v in rg], dtype=torch.int64)
+            allr = [torch.zeros_like(flat) for _ in range(self.world)]
+            dist.all_gather(allr, flat, group=self.group)
+            ranges = []
+            for r in range(self.world):
+                a = allr[r].cpu().numpy()
+                ranges.append([(int(a[2 * i]), int(a[2 * i + 1])) for i in range(int(ks[r].item()))])
+            rows = [sum(c for _, c in rg) for rg in ranges]
+            self._layout = (ranges, rows, max(1, max(rows)))
+        return self._layout
+
+    def predict_tree_gathered(self, root_only=False):
+        """Runs the downward pass for this rank's subtrees and gathers every rank's rows: returns device tensors
+        (mean, var) of all N locations in TREE order on every rank (root_only: on group rank 0, None elsewhere)."""
+        import torch
+        import torch.distributed as dist
+        ranges, rows, pad = self._gather_layout()
+        pack = torch.zeros(2, pad, dtype=torch.float64, device=self.dev)
+        mine = rows[self.rank]
+        if mine:
+            tmp = torch.empty(2 * mine, dtype=torch.float64, device=self.dev)
+            self.check(self.lib.mra_run_predict_pack_dev(self.h, self.stream(), C.c_void_p(tmp.data_ptr()), mine))
+            pack[:, :mine] = tmp.view(2, mine)
+        if root_only:
+            dst = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            got = [torch.empty_like(pack) for _ in range(self.world)] if self.rank == 0 else None
+            dist.gather(pack, got, dst=dst, group=self.group)
+            if self.rank != 0:
+                return None, None
+        else:
+            got = torch.empty(self.world, 2, pad, dtype=torch.float64, device=self.dev)
+            dist.all_gather_into_tensor(got, pack, group=self.group)
+        full = torch.empty(2, self.N, dtype=torch.float64, device=self.dev)
+        for r in range(self.world):
+            off = 0
+            for start, cnt in ranges[r]:
+                full[:, start:start + cnt] = got[r][:, off:off + cnt]
+                off += cnt
+        return full[0], full[1]
+
     def predict(self):
         if self.shard_level:
             import torch
-            import torch.distributed as dist
-            out = torch.empty(2, self.N, dtype=torch.float64, device=self.dev)
-            self.predict_dev(out[0], out[1])
-            if self.gather == "root":
-                dist.reduce(out, dst=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
-                            group=self.group)
-            else:
-                dist.all_reduce(out, group=self.group)
-            self.fetch_likelihood()                           # surfaces a non-SPD status like the plain path
-            if self.gather == "root" and self.rank != 0:
+            mt, vt = self.predict_tree_gathered(root_only=(self.gather == "root"))
+            self.fetch_likelihood()                           # surfaces a non-SPD status like the plain path (collective)
+            if mt is None:
                 return None, None
+            out = torch.empty(2, self.N, dtype=torch.float64, device=self.dev)
+            self.check(self.lib.mra_unpermute_tree_dev(self.h, self.stream(), C.c_void_p(mt.data_ptr()),
+                                                       C.c_void_p(vt.data_ptr()), C.c_void_p(out[0].data_ptr()),
+                                                       C.c_void_p(out[1].data_ptr())))
             host = torch.empty(2, self.N, dtype=torch.float64, pin_memory=True)
             host.copy_(out)
             res = host.numpy()
@@ -242,17 +300,20 @@ class DeviceSession(object):
         return host[0], host[1]
 
     def predict_dev(self, mean_t=None, sd_t=None, reduce=False):
-        """Results into device tensors (caller's order).  Sharded: each rank fills its own rows and zeros
-        elsewhere; reduce=True sum-reduces them so every rank holds all N results."""
+        """Results into device tensors (caller's order).  Sharded without reduce: each rank fills its own rows and
+        zeros elsewhere; reduce=True: the ranks' rows are gathered (16 B per location) so that every rank holds all N
+        results."""
+        if reduce and self.shard_level and self._collective:
+            if mean_t is None or sd_t is None:
+                raise ValueError("reduce=True needs caller-owned output tensors")
+            mt, vt = self.predict_tree_gathered()
+            self.check(self.lib.mra_unpermute_tree_dev(self.h, self.stream(), C.c_void_p(mt.data_ptr()),
+                                                       C.c_void_p(vt.data_ptr()), C.c_void_p(mean_t.data_ptr()),
+                                                       C.c_void_p(sd_t.data_ptr())))
+            return
         pm = C.c_void_p(mean_t.data_ptr()) if mean_t is not None else None
         ps = C.c_void_p(sd_t.data_ptr()) if sd_t is not None else None
         self.check(self.lib.mra_run_predict_dev(self.h, self.stream(), pm, ps))
-        if reduce and self.shard_level:
-            import torch.distributed as dist
-            if mean_t is None or sd_t is None:
-                raise ValueError("reduce=True needs caller-owned output tensors")
-            dist.all_reduce(mean_t, group=self.group)
-            dist.all_reduce(sd_t, group=self.group)
 
     def keep_posterior_basis(self, on=True):
         """Diagnostics (pymra_b200/diagnostics.py): the next predict pass keeps every level's folded posterior basis."""
