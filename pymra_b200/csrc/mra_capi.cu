@@ -145,7 +145,7 @@ namespace {
 // Splits [0, n) over a few host threads (the host-side O(N) passes of plan / set_structure).
 template <class F>
 void parallel_for(int64_t n, F fn) {
-  unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
   if (const char* e = std::getenv("MRA_HOST_THREADS")) nt = (unsigned)std::max(1, std::min((int)nt, std::atoi(e)));
   if (n < (int64_t)1 << 18 || nt == 1) {
     fn((int64_t)0, n);
@@ -853,11 +853,27 @@ void build_lists(mra_handle* h) {
         else kr.push_back(Range{ko, h->r});
       }
       last = -1;
-      for (int i = 0; i < h->n_regular_tiles[m]; ++i) {
-        const int pp = part_of[h->ptiles_at[m][i].x];
-        if (pp < last) ok = false;
-        last = pp;
-        extend(h->part_tiles[m][pp], i);
+      {
+        // the tiles of a node are consecutive: walk the list node run by node run (N / 64 tiles per level)
+        const std::vector<int4>& tl = h->ptiles_at[m];
+        const int nreg = h->n_regular_tiles[m];
+        int i = 0;
+        while (i < nreg) {
+          const int node = tl[i].x;
+          // a node's run is at most ceil(rows / 64) tiles long; pieces of a replicated node (sharded) form shorter runs
+          int j = i + 1;
+          const int64_t cap = i + (h->row_count[node] + TB - 1) / TB;
+          if (cap <= nreg && cap > i && tl[cap - 1].x == node && (cap == nreg || tl[cap].x != node)) j = (int)cap;
+          else
+            while (j < nreg && tl[j].x == node) ++j;
+          const int pp = part_of[node];
+          if (pp < last) ok = false;
+          last = pp;
+          Range& rg = h->part_tiles[m][pp];
+          if (rg.count == 0) rg.begin = i;
+          rg.count += j - i;
+          i = j;
+        }
       }
       if (h->n_regular_tiles[m] != (int)h->ptiles_at[m].size()) ok = false;   // gathered tiles below level 0: s > 2
     }
@@ -1090,7 +1106,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
     const int64_t* rc = h->row_count.data();
     auto over_leaves = [&](auto fn) {
       // parallel_for splits an index range; give it the leaves
-      unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+      unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
       if (const char* e = std::getenv("MRA_HOST_THREADS")) nt = (unsigned)std::max(1, std::min((int)nt, std::atoi(e)));
       if (nl < 1024 || nt == 1) {
         fn((int64_t)0, nl);
