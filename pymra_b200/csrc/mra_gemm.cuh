@@ -132,9 +132,14 @@ __device__ __forceinline__ void stage_load(double* st, const double* const* rows
 // (Skipping the all-zero column groups of a triangular B operand with a per-group predicate was measured SLOWER, twice:
 // r01g for ragged column counts, r04e for the Linv / Lp^-1 operands -- predict_fused 43.7 -> 50.3 ms.  The unrolled,
 // unpredicated DMMA stream is worth more than the 37 % of the flops such a segment could save.)
-template <int NJ, class GA, class GB>
-__device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows = TB, int ncols = TB) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// J0: first column group that is computed.  A chunk of a LOWER-TRIANGULAR B operand (B[j][k] = 0 for k > j: Linv,
+// Lp^-1) whose k range starts at 16 t has only zeros in the column groups below 2 t; chunk_mma_tri picks the unrolled
+// variant for that chunk with one warp-uniform switch, so the DMMA stream itself stays free of predicates.
+template <int NJ, int J0 = 0, class GA, class GB>
+__device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows = TB, int ncols = TB, int wg = -1) {
+  // wg: the 16-row group this warp owns (default: its index).  Kernels whose warps do unequal work (ragged or
+  // triangular tiles) rotate it with the CTA index so that the idle tensor pipe differs between co-resident CTAs.
+  const int lane = threadIdx.x & 31, warp = wg >= 0 ? wg : (int)(threadIdx.x >> 5);
   const int wm = warp * 16;
   if (wm >= mrows) return;
   (void)ncols;
@@ -145,12 +150,27 @@ __device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows
 #pragma unroll
     for (int i = 0; i < 2; ++i) a[i] = ga(wm + i * 8 + g, ks + q);
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) b[j] = gb(j * 8 + g, ks + q);
+    for (int j = J0; j < NJ; ++j) b[j] = gb(j * 8 + g, ks + q);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) dmma884(acc.v[i][j], a[i], b[j]);
+      for (int j = J0; j < NJ; ++j) dmma884(acc.v[i][j], a[i], b[j]);
   }
+}
+
+// tl: index of the chunk inside the triangular segment (k range [16 tl, 16 tl + 16)); the segment is at most 8 NJ long.
+template <int NJ, class GA, class GB>
+__device__ __forceinline__ void chunk_mma_tri(AccT<NJ>& acc, GA ga, GB gb, int tl, int mrows = TB) {
+  if constexpr (NJ > 6) {
+    if (tl == 3) return chunk_mma<NJ, 6>(acc, ga, gb, mrows);
+  }
+  if constexpr (NJ > 4) {
+    if (tl == 2) return chunk_mma<NJ, 4>(acc, ga, gb, mrows);
+  }
+  if constexpr (NJ > 2) {
+    if (tl == 1) return chunk_mma<NJ, 2>(acc, ga, gb, mrows);
+  }
+  if (tl == 0) chunk_mma<NJ, 0>(acc, ga, gb, mrows);
 }
 
 // acc += A B^T.
@@ -225,9 +245,13 @@ struct NoGen {
   __device__ double operator()(int, int) const { return 0.0; }
 };
 
-template <int VEC, bool GEN = false, bool CACHE_PTRS = true, int NJ, class FA, class FB, class FK, class SM, class FG = NoGen>
+// TRI: the chunks [tri_kt0, tri_kt0 + tri_nk) of the stream belong to a segment whose B operand is lower triangular
+// (B row j zero beyond column j, j = tile column): their all-zero column groups are skipped (chunk_mma_tri).
+template <int VEC, bool GEN = false, bool CACHE_PTRS = true, bool TRI = false, int NJ, class FA, class FB, class FK, class SM,
+          class FG = NoGen>
 __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB fb, FK fk, SM& sm,
-                                              const double* dummy, int mrows = TB, int ncols = TB, FG fg = FG()) {
+                                              const double* dummy, int mrows = TB, int ncols = TB, FG fg = FG(),
+                                              int tri_kt0 = 0, int tri_nk = 0) {
   constexpr int BR = 8 * NJ;            // rows of the B operand that exist
   constexpr int BI = (BR + 15) / 16;    // 16-row groups of B a thread copies (16-byte path)
   __syncthreads();
@@ -316,8 +340,10 @@ __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB
     }
     const double* sa = sm.a[buf];
     const double* sb = sm.b[buf];
-    chunk_mma(acc, [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; },
-              [&](int row, int kk) -> double { return sb[stage_pos(row, kk)]; }, mrows, ncols);
+    auto ga = [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; };
+    auto gb = [&](int row, int kk) -> double { return sb[stage_pos(row, kk)]; };
+    if (TRI && (unsigned)(kt - tri_kt0) < (unsigned)tri_nk) chunk_mma_tri(acc, ga, gb, kt - tri_kt0, mrows);
+    else chunk_mma(acc, ga, gb, mrows, ncols);
     if (++buf == NSTAGE) buf = 0;
   }
   cp_async_wait<0>();
@@ -329,9 +355,13 @@ __device__ __forceinline__ int kstage_pos(int kr, int n) { return kr * TB + (n ^
 // acc += A * B with A K-contiguous rows in global memory (fa(rr) -> row pointer) and B K-major in global
 // memory: B[k][n] = bbase[k * ldb + n], k < K, n < ncols (zero outside).  Used where the contraction index
 // is the row index of a stored block (left-multiplication of a block by a small matrix).
+// wg: row group of this warp (see chunk_mma).  tri_row0: the A operand is lower triangular, A[tile row i][k] = 0 for
+// k > tri_row0 + i; a warp skips the chunks that lie entirely beyond its 16 rows (default: never).
 template <int VEC, int NJ, class FA, class SM>
 __device__ __forceinline__ void tile_gemm_kmajorB(AccT<NJ>& acc, int K, FA fa, const double* bbase, long long ldb,
-                                                  int ncols, SM& sm, const double* dummy) {
+                                                  int ncols, SM& sm, const double* dummy, int wg = -1,
+                                                  int tri_row0 = 1 << 30) {
+  const int klast = tri_row0 + (wg >= 0 ? wg : (int)(threadIdx.x >> 5)) * 16 + 15;     // last k with a nonzero in my rows
   __syncthreads();
   if (threadIdx.x < TB) sm.row_a[0][threadIdx.x] = fa((int)threadIdx.x);
   __syncthreads();
@@ -379,8 +409,9 @@ __device__ __forceinline__ void tile_gemm_kmajorB(AccT<NJ>& acc, int K, FA fa, c
     }
     const double* sa = sm.a[buf];
     const double* sb = sm.b[buf];
-    chunk_mma(acc, [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; },
-              [&](int col, int kk) -> double { return sb[kstage_pos(kk, col)]; });
+    if (kt * KC <= klast)
+      chunk_mma(acc, [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; },
+                [&](int col, int kk) -> double { return sb[kstage_pos(kk, col)]; }, TB, TB, wg);
     if (++buf == NSTAGE) buf = 0;
   }
   cp_async_wait<0>();
@@ -390,7 +421,9 @@ __device__ __forceinline__ void tile_gemm_kmajorB(AccT<NJ>& acc, int K, FA fa, c
 // rowk[k][col0 + n]), nullptr = zero row.  rowk lives in shared memory and holds at least K entries.
 template <int VEC, int NJ, class FA, class SM>
 __device__ __forceinline__ void tile_gemm_kmajorB_rows(AccT<NJ>& acc, int K, FA fa, const double* const* rowk, int ncols,
-                                                       SM& sm, const double* dummy, int col0 = 0) {
+                                                       SM& sm, const double* dummy, int col0 = 0, int wg = -1,
+                                                       int tri_row0 = 1 << 30, int mrows = TB) {
+  const int klast = tri_row0 + (wg >= 0 ? wg : (int)(threadIdx.x >> 5)) * 16 + 15;
   __syncthreads();
   if (threadIdx.x < TB) sm.row_a[0][threadIdx.x] = fa((int)threadIdx.x);
   __syncthreads();
@@ -440,8 +473,9 @@ __device__ __forceinline__ void tile_gemm_kmajorB_rows(AccT<NJ>& acc, int K, FA 
     }
     const double* sa = sm.a[buf];
     const double* sb = sm.b[buf];
-    chunk_mma(acc, [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; },
-              [&](int col, int kk) -> double { return sb[kstage_pos(kk, col)]; });
+    if (kt * KC <= klast)
+      chunk_mma(acc, [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; },
+                [&](int col, int kk) -> double { return sb[kstage_pos(kk, col)]; }, mrows, TB, wg);
     if (++buf == NSTAGE) buf = 0;
   }
   cp_async_wait<0>();
@@ -528,8 +562,8 @@ __device__ __forceinline__ void tile_transform(AccT<NJ>& acc, F f) {
 
 // f(row, col, value) for every accumulator element owned by this thread.
 template <int NJ, class F>
-__device__ __forceinline__ void tile_epilogue(const AccT<NJ>& acc, F f) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void tile_epilogue(const AccT<NJ>& acc, F f, int wg = -1) {
+  const int lane = threadIdx.x & 31, warp = wg >= 0 ? wg : (int)(threadIdx.x >> 5);
   const int wm = warp * 16;
   const int g = lane >> 2, q = lane & 3;
 #pragma unroll
