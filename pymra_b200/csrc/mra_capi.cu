@@ -263,6 +263,10 @@ DevCtx make_ctx(mra_handle* h) {
   c.status = at<int>(h, L.status);
   c.P = at<DevParams>(h, L.params);
   c.chol_mma = h->chol_mma ? 1 : 0;
+  {
+    static const int tune = [] { const char* e = std::getenv("MRA_TUNE"); return e ? std::atoi(e) : 0; }();
+    c.tune = tune;
+  }
   c.keep_t0 = h->keep_t0 ? 1 : 0;
   c.leaf_v2 = h->leaf_v2 ? 1 : 0;
   c.LS = at<double>(h, L.LS);

@@ -135,7 +135,7 @@ __device__ __forceinline__ void stage_load(double* st, const double* const* rows
 // J0: first column group that is computed.  A chunk of a LOWER-TRIANGULAR B operand (B[j][k] = 0 for k > j: Linv,
 // Lp^-1) whose k range starts at 16 t has only zeros in the column groups below 2 t; chunk_mma_tri picks the unrolled
 // variant for that chunk with one warp-uniform switch, so the DMMA stream itself stays free of predicates.
-template <int NJ, int J0 = 0, class GA, class GB>
+template <int NJ, int J0 = 0, int J1 = NJ, class GA, class GB>
 __device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows = TB, int ncols = TB, int wg = -1) {
   // wg: the 16-row group this warp owns (default: its index).  Kernels whose warps do unequal work (ragged or
   // triangular tiles) rotate it with the CTA index so that the idle tensor pipe differs between co-resident CTAs.
@@ -150,12 +150,22 @@ __device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows
 #pragma unroll
     for (int i = 0; i < 2; ++i) a[i] = ga(wm + i * 8 + g, ks + q);
 #pragma unroll
-    for (int j = J0; j < NJ; ++j) b[j] = gb(j * 8 + g, ks + q);
+    for (int j = J0; j < J1; ++j) b[j] = gb(j * 8 + g, ks + q);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = J0; j < NJ; ++j) dmma884(acc.v[i][j], a[i], b[j]);
+      for (int j = J0; j < J1; ++j) dmma884(acc.v[i][j], a[i], b[j]);
   }
+}
+
+// Diagonal tile of a symmetric product (64 x 64 tile, NJ = 8): the warp owning row group wg only needs the column
+// groups up to its own rows, 0 .. 2 wg + 1; the caller mirrors the lower part.
+template <class GA, class GB>
+__device__ __forceinline__ void chunk_mma_lower(AccT<8>& acc, GA ga, GB gb, int mrows, int wg) {
+  if (wg == 0) return chunk_mma<8, 0, 2>(acc, ga, gb, mrows, TB, wg);
+  if (wg == 1) return chunk_mma<8, 0, 4>(acc, ga, gb, mrows, TB, wg);
+  if (wg == 2) return chunk_mma<8, 0, 6>(acc, ga, gb, mrows, TB, wg);
+  chunk_mma<8, 0, 8>(acc, ga, gb, mrows, TB, wg);
 }
 
 // tl: index of the chunk inside the triangular segment (k range [16 tl, 16 tl + 16)); the segment is at most 8 NJ long.
@@ -177,9 +187,9 @@ __device__ __forceinline__ void chunk_mma_tri(AccT<NJ>& acc, GA ga, GB gb, int t
 //   A_GLOBAL: fa(rr) -> const double* row pointer (nullptr = zero row); else fa(rr, k) -> element
 //   (shared-memory resident operand; must return 0 for k >= K).  Same for B.
 // Must be called by all 128 threads; safe to call back to back (leading barrier).
-template <int VEC, bool A_GLOBAL, bool B_GLOBAL, int NJ, class FA, class FB, class SM>
+template <int VEC, bool A_GLOBAL, bool B_GLOBAL, bool LOWER = false, int NJ, class FA, class FB, class SM>
 __device__ __forceinline__ void tile_gemm(AccT<NJ>& acc, int K, FA fa, FB fb, SM& sm, const double* dummy,
-                                          int mrows = TB, int ncols = TB) {
+                                          int mrows = TB, int ncols = TB, int wg = -1, bool lower = false) {
   constexpr int BR = 8 * NJ;     // rows of the B operand (= columns of the tile) that exist
   __syncthreads();   // previous users of the stages / row tables (and of resident operands) are done
   if (A_GLOBAL) {
@@ -230,7 +240,10 @@ __device__ __forceinline__ void tile_gemm(AccT<NJ>& acc, int K, FA fa, FB fb, SM
       if constexpr (B_GLOBAL) return sb[stage_pos(row, kk)];
       else return fb(row, k0 + kk);
     };
-    chunk_mma(acc, ga, gb, mrows, ncols);
+    if constexpr (LOWER && NJ == 8) {
+      if (lower) chunk_mma_lower(acc, ga, gb, mrows, wg);      // diagonal tile of a symmetric product
+      else chunk_mma(acc, ga, gb, mrows, ncols, wg);
+    } else chunk_mma(acc, ga, gb, mrows, ncols, wg);
     if (++buf == NSTAGE) buf = 0;
   }
   cp_async_wait<0>();
@@ -247,11 +260,13 @@ struct NoGen {
 
 // TRI: the chunks [tri_kt0, tri_kt0 + tri_nk) of the stream belong to a segment whose B operand is lower triangular
 // (B row j zero beyond column j, j = tile column): their all-zero column groups are skipped (chunk_mma_tri).
+// wg >= 0: row group of this warp (see chunk_mma); lower: only the column groups up to the warp's own rows are computed
+// (diagonal tile of a symmetric product, NJ = 8).
 template <int VEC, bool GEN = false, bool CACHE_PTRS = true, bool TRI = false, int NJ, class FA, class FB, class FK, class SM,
           class FG = NoGen>
 __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB fb, FK fk, SM& sm,
                                               const double* dummy, int mrows = TB, int ncols = TB, FG fg = FG(),
-                                              int tri_kt0 = 0, int tri_nk = 0) {
+                                              int tri_kt0 = 0, int tri_nk = 0, int wg = -1, bool lower = false) {
   constexpr int BR = 8 * NJ;            // rows of the B operand that exist
   constexpr int BI = (BR + 15) / 16;    // 16-row groups of B a thread copies (16-byte path)
   __syncthreads();
@@ -343,7 +358,10 @@ __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB
     auto ga = [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; };
     auto gb = [&](int row, int kk) -> double { return sb[stage_pos(row, kk)]; };
     if (TRI && (unsigned)(kt - tri_kt0) < (unsigned)tri_nk) chunk_mma_tri(acc, ga, gb, kt - tri_kt0, mrows);
-    else chunk_mma(acc, ga, gb, mrows, ncols);
+    else if constexpr (NJ == 8 && !TRI && !GEN) {
+      if (lower) chunk_mma_lower(acc, ga, gb, mrows, wg);
+      else chunk_mma(acc, ga, gb, mrows, ncols, wg);
+    } else chunk_mma(acc, ga, gb, mrows, ncols, wg);
     if (++buf == NSTAGE) buf = 0;
   }
   cp_async_wait<0>();
