@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -56,6 +57,9 @@ struct Layout {
 struct mra_handle {
   int device = 0;
   std::string err;
+  // build_lists runs as a background job from mra_set_structure / mra_set_shard on (it depends on the tree only);
+  // mra_plan joins it after its own O(N) passes over the observations
+  std::future<void> lists_job;
   bool has_structure = false, planned = false, bound = false, uploaded = false, lik_done = false,
        pred_done = false, want_predict = false;
   // structure
@@ -946,6 +950,7 @@ int mra_create(mra_handle** out, int device) {
 }
 
 int mra_destroy(mra_handle* h) {
+  if (h && h->lists_job.valid()) h->lists_job.get();
   if (h && h->copy_stream) {
     DevGuard g(h->device);
     cudaEventDestroy(h->copy_event);
@@ -966,8 +971,19 @@ int mra_destroy(mra_handle* h) {
 
 const char* mra_last_error(const mra_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
+namespace {
+void wait_lists(mra_handle* h) {
+  if (h->lists_job.valid()) h->lists_job.get();
+}
+void start_lists(mra_handle* h) {
+  if (std::getenv("MRA_SYNC_LISTS")) build_lists(h);
+  else h->lists_job = std::async(std::launch::async, [h] { build_lists(h); });
+}
+}  // namespace
+
 int mra_set_structure(mra_handle* h, const mra_structure* s) {
   if (!h || !s) return MRA_ERR_ARG;
+  wait_lists(h);
   if (s->n_locs <= 0 || s->n_locs >= (int64_t(1) << 31)) return fail(h, MRA_ERR_ARG, "n_locs out of range");
   if (s->dim != 1 && s->dim != 2) return fail(h, MRA_ERR_ARG, "dim must be 1 or 2");
   if (s->r < 1 || s->r > 128) return fail(h, MRA_ERR_ARG, "r must be in [1, 128] in this build");
@@ -1036,11 +1052,11 @@ int mra_set_structure(mra_handle* h, const mra_structure* s) {
   tr.mark("perm + validation");
   h->shard_level = 0;
   h->role.assign(nn, 1);
-  build_lists(h);
-  tr.mark("build_lists");
   h->ldv = std::max<long long>(2, ((long long)std::max(h->depth, 1) * h->r + 1) / 2 * 2);
   h->has_structure = true;
   h->planned = h->bound = h->uploaded = h->lik_done = h->pred_done = false;
+  start_lists(h);
+  tr.mark("build_lists started");
   return MRA_OK;
 }
 
@@ -1162,6 +1178,8 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
     });
   }
   tr.mark("leaf row lists");
+  wait_lists(h);
+  tr.mark("wait for build_lists");
   std::vector<double> my_rows_prior((size_t)nn, 0.0), my_rows_pred((size_t)nn, 0.0);
   for (size_t m = 0; m < h->ptiles_at.size(); ++m)
     for (size_t i = 0; i < h->ptiles_at[m].size(); ++i) {
@@ -1585,6 +1603,7 @@ int mra_run_graph(mra_handle* h, void* stream, int with_predict) {
 int mra_set_shard(mra_handle* h, int32_t shard_level, const int8_t* node_role) {
   if (!h) return MRA_ERR_ARG;
   if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
+  wait_lists(h);
   if (shard_level == 0) {
     h->shard_level = 0;
     h->role.assign(h->n_nodes, 1);
@@ -1603,7 +1622,7 @@ int mra_set_shard(mra_handle* h, int32_t shard_level, const int8_t* node_role) {
   drop_graph(h);
   h->slot_base = shard_level ? h->level_off[shard_level] : 0;
   h->n_slots = shard_level ? h->level_off[shard_level + 1] - h->level_off[shard_level] : 0;
-  build_lists(h);
+  start_lists(h);
   h->planned = h->bound = h->uploaded = h->lik_done = h->pred_done = false;
   return MRA_OK;
 }

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest_exit=$?
+tail -3 gpurun_out/pytest_gpu.log
+for t in 0 8; do MRA_TUNE=$t python tools/profile_step.py --workload cfg5 --warm 2 > gpurun_out/tune_$t.json 2>&1; done
+MRA_HOST_TRACE=1 python bench.py --steps 3 --warmup 3 --e2e-steps 3 --no-cpu-baseline > gpurun_out/bench_cfg5.json 2> gpurun_out/bench_cfg5.err; echo bench_exit=$?
