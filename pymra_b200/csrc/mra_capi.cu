@@ -285,7 +285,16 @@ size_t smem_cholinv(int n) {     // the larger of the two chol_inv_block variant
   return sizeof(double) * std::max((size_t)n * (n + 1) + n + NT * 9 + 8, chol_mma_smem_doubles(n));
 }
 size_t smem_prior(int r) { return sizeof(GemmSmemT<2>) + sizeof(double) * ((size_t)2 * r + 2 * TB) + sizeof(int) * TB; }
-size_t smem_pgroups(int r) { return sizeof(PriorSmem) + sizeof(double) * ((size_t)2 * r + 2 * PG * TB); }
+// MRA_SMEM_PAD_PRIOR / MRA_SMEM_PAD_PREDICT (bytes): extra dynamic shared memory, an A/B knob that lowers the number of
+// co-resident CTAs of the two heaviest kernels without touching their code
+size_t env_pad(const char* name) {
+  const char* e = std::getenv(name);
+  return e ? (size_t)std::max(0, std::atoi(e)) : 0;
+}
+size_t smem_pgroups(int r) {
+  static const size_t pad = env_pad("MRA_SMEM_PAD_PRIOR");
+  return sizeof(PriorSmem) + sizeof(double) * ((size_t)2 * r + 2 * PG * TB) + pad;
+}
 size_t smem_ut2(int max_obs) { return GS1 + sizeof(double*) * (size_t)((max_obs + TB - 1) / TB * TB); }
 size_t smem_leafq(int max_obs) {
   return sizeof(GemmSmemT<2>) + sizeof(double) * ((size_t)3 * max_obs + 2 * TB) + sizeof(int) * TB + 16;
@@ -298,8 +307,9 @@ size_t smem_solve() { return GS1; }
 size_t smem_plain() { return sizeof(GemmSmemT<4>); }   // k_assemble_A: up to 4 children per product
 size_t smem_predict(int r, int depth) {
   int ldT = ((r + 15) / 16) * 16 + 4;
+  static const size_t pad = env_pad("MRA_SMEM_PAD_PREDICT");
   return GS + sizeof(double) * ((size_t)(r > TB ? TB * ldT : 0) + 2 * TB + (size_t)std::max(depth, 1) * r) +
-         sizeof(int) * MAX_LEVELS + sizeof(long long) * 2 * MAX_LEVELS;
+         sizeof(int) * MAX_LEVELS + sizeof(long long) * 2 * MAX_LEVELS + pad;
 }
 
 // Kernels are instantiated for VEC = 2 (16-byte cp.async, even r) and VEC = 1 (odd r).
