@@ -130,6 +130,24 @@ int mra_plan(mra_handle *h, const double *obs, int want_predict, size_t *workspa
  * (a torch uint8 tensor in the Python host). */
 int mra_bind_workspace(mra_handle *h, void *dev_workspace, size_t bytes);
 
+/* The same set-up in two parts (unsharded handles), for callers that want the device to start on the prior pass
+ * (MRANode.py:73-80, 378-395: knots and locations only) while the host is still scanning the observations
+ * (MRANode.py:415): the arena is split into a tree-dependent part (work lists, the basis slab, every per-internal-node
+ * block) and an observation-dependent part (the leaves' observed / unobserved row lists and per-leaf blocks), two
+ * allocations owned by the caller.
+ *   mra_plan_tree  sizes the tree part;
+ *   mra_bind_tree  binds it, uploads the tree tables and permutes the inputs (dev_locs / dev_obs as in
+ *                  mra_upload_data_dev): mra_set_cov / mra_set_nugget, mra_stream_begin_async and
+ *                  mra_stream_part_prior_async may follow;
+ *   mra_plan_obs   scans the NaN pattern and sizes the observation part;
+ *   mra_bind_obs   binds it and uploads its tables on a side stream (`stream` waits for them): the handle is then in the
+ *                  state mra_plan + mra_bind_workspace + mra_upload_data leave it in. */
+int mra_plan_tree(mra_handle *h, int want_predict, size_t *tree_bytes);
+int mra_bind_tree(mra_handle *h, void *dev_workspace_tree, size_t bytes, const double *dev_locs, const double *dev_obs,
+                  void *stream);
+int mra_plan_obs(mra_handle *h, const double *obs, size_t *obs_bytes);
+int mra_bind_obs(mra_handle *h, void *dev_workspace_obs, size_t bytes, void *stream);
+
 /* locs: [N*dim] row-major (MRATree locs), obs: [N] with NaN = missing (MRATree obs).
  * Host buffers; copied H2D on `stream` and permuted to tree order on the device. */
 int mra_upload_data(mra_handle *h, const double *locs, const double *obs, void *stream);
@@ -213,6 +231,9 @@ int mra_run_likelihood_top_async(mra_handle *h, void *stream, const double *dev_
 int mra_stream_parts(const mra_handle *h, int32_t *n_parts);
 int mra_stream_begin_async(mra_handle *h, void *stream, const int64_t *knot_rows);
 int mra_stream_part_async(mra_handle *h, void *stream, int32_t part, const int64_t *knot_rows);
+/* Only the prior levels >= 1 of the part (allowed after mra_bind_tree, before the observation part is bound);
+ * a later mra_stream_part_async(part) runs the rest. */
+int mra_stream_part_prior_async(mra_handle *h, void *stream, int32_t part, const int64_t *knot_rows);
 int mra_stream_end_async(mra_handle *h, void *stream);
 /* Sharded handles (shard level 1: 2-4 GPUs, the parts ARE the shards; level 2: up to 16 GPUs, a part is shared
  * by the ranks that own subtrees inside it) stream the same way: every rank calls mra_stream_begin_async (root

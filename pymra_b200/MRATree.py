@@ -191,9 +191,12 @@ class MRATree(object):
             ok = sb.wait(0)
             t2 = time.perf_counter()
             nparts = 0
+            two_part = world == 1 and os.environ.get("PYMRA_B200_TWO_PART", "1") != "0"
             if ok:
+                # one GPU: only the tree-dependent half of the set-up now -- the root's prior level (and the first
+                # subtree's, once its knots are there) run while the host scans the observations (finish_plan)
                 session = DeviceSession(sb.structure, locs_c, obs_arr, want_predict=True, device=device, group=group,
-                                        gather=gather, staged=staged)
+                                        gather=gather, staged=staged, two_part=two_part)
                 session.set_params(self._cov, self._R)
                 nparts = session.n_parts()
             del staged
@@ -207,6 +210,12 @@ class MRATree(object):
                 tw = time.perf_counter()
                 ok = sb.wait(1 + c) and ok
                 waits += time.perf_counter() - tw
+                if c == 0 and session is not None:
+                    if ok and streamable and c in mine and two_part:
+                        session.stream_part_prior(c)
+                    tp = time.perf_counter()
+                    session.finish_plan()
+                    self.timings["finish_plan"] = time.perf_counter() - tp
                 if ok and streamable and c in mine:
                     session.stream_part(c)
             tw = time.perf_counter()

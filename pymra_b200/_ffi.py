@@ -45,6 +45,10 @@ SIGNATURES = {
     "mra_set_structure": (C.c_int, [C.c_void_p, C.POINTER(MraStructure)]),
     "mra_plan": (C.c_int, [C.c_void_p, _pd, C.c_int, C.POINTER(C.c_size_t)]),
     "mra_bind_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mra_plan_tree": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
+    "mra_bind_tree": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mra_plan_obs": (C.c_int, [C.c_void_p, _pd, C.POINTER(C.c_size_t)]),
+    "mra_bind_obs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mra_upload_data": (C.c_int, [C.c_void_p, _pd, _pd, C.c_void_p]),
     "mra_upload_data_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mra_set_cov": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
@@ -66,6 +70,7 @@ SIGNATURES = {
     "mra_stream_parts": (C.c_int, [C.c_void_p, _p32]),
     "mra_stream_begin_async": (C.c_int, [C.c_void_p, C.c_void_p, _p64]),
     "mra_stream_part_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _p64]),
+    "mra_stream_part_prior_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _p64]),
     "mra_stream_end_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mra_stream_my_parts": (C.c_int, [C.c_void_p, _p32]),
     "mra_stream_end_local_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

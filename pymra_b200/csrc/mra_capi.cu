@@ -60,6 +60,9 @@ struct mra_handle {
   // build_lists runs as a background job from mra_set_structure / mra_set_shard on (it depends on the tree only);
   // mra_plan joins it after its own O(N) passes over the observations
   std::future<void> lists_job;
+  bool tree_planned = false, tree_bound = false, split_arena = false;      // two-part plan (mra_plan_tree / mra_plan_obs)
+  size_t total_A = 0, total_B = 0;
+  Layout lay_b{};                                                          // part B, offsets relative to its start
   bool has_structure = false, planned = false, bound = false, uploaded = false, lik_done = false,
        pred_done = false, want_predict = false;
   // structure
@@ -109,6 +112,7 @@ struct mra_handle {
   std::vector<Range> part_gtiles;                           // [part] -> gathered tiles of its level-1 node in ptiles_at[0]
   std::vector<int2> part_gather;                            // [part] -> (level-1 top node, first slot in gather_rows) or (-1, 0)
   int stream_parts_done = 0;                                // bit mask of the parts run since mra_stream_begin_async
+  int stream_prior_done = 0;                                // parts whose prior levels have run (mra_stream_part_prior_async)
   int my_parts = 0;                                         // bit mask of the parts this rank evaluates (all when unsharded)
   bool stream_open = false, leafq_done = false;
   cudaStream_t copy_stream = nullptr;
@@ -713,6 +717,7 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
 // (role 1) in full, the replicated top (role >= 2) restricted to the rows of my subtrees and of top-level
 // leaves, plus the rows of the top nodes' knots that lie in other ranks' subtrees (needed by knot_factor).
 void build_lists(mra_handle* h) {
+  HostTrace tr("build_lists");
   const int nn = h->n_nodes, s = h->shard_level;
   const size_t nlev = (size_t)h->depth + 1;
   h->internal_at.assign(nlev, {});
@@ -800,6 +805,7 @@ void build_lists(mra_handle* h) {
     h->internal_at.pop_back();
     h->ptiles_at.pop_back();
   }
+  tr.mark("tiles");
   // groups of the regular prior tiles: consecutive full tiles of one node, at most PG per group
   h->pgroups_at.assign(h->ptiles_at.size(), {});
   h->group_of_tile.assign(h->ptiles_at.size(), {});
@@ -824,10 +830,12 @@ void build_lists(mra_handle* h) {
     }
   });
   for (auto& t : gth) t.join();
+  tr.mark("groups");
   h->leaf_tiles.clear();
   for (int n : h->leaves)
     for (int64_t r0 = 0; r0 < h->row_count[n]; r0 += TB)
       h->leaf_tiles.push_back(make_int4(n, (int)(h->row_start[n] + r0), (int)std::min<int64_t>(TB, h->row_count[n] - r0), 0));
+  tr.mark("leaf tiles");
   // parts for the streamed evaluation: the subtree of every child of the root is a contiguous range of each list.
   // Unsharded: every part is mine.  Sharded at level 1: the parts are the shards.  Sharded at level 2: a part is
   // mine when one of my subtrees lies in it; its level-1 node is a replicated top node whose gathered knot tiles
@@ -1070,24 +1078,160 @@ int mra_set_structure(mra_handle* h, const mra_structure* s) {
   return MRA_OK;
 }
 
-int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspace_bytes) {
-  if (!h || !obs || !workspace_bytes) return MRA_ERR_ARG;
-  if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
-  HostTrace tr("plan");
+// The plan has a tree-dependent part (node table of the internal nodes, work lists, the basis slab V and every
+// per-internal-node block: "part A" of the arena) and an observation-dependent part (NaN scan, the leaves' observed /
+// unobserved row lists, the per-leaf blocks: "part B").  mra_plan lays both out in ONE arena.  mra_plan_tree /
+// mra_bind_tree / mra_plan_obs / mra_bind_obs expose the two halves, so that a caller can start the prior pass (which
+// needs part A only) while the host is still scanning the observations.
+namespace {
+
+struct LeafOffsets {
+  long long s_off = 0, di_off = 0, ut_off = 0, qt_off = 0, utt_off = 0;
+};
+
+int plan_tree_impl(mra_handle* h, int want_predict) {
+  HostTrace tr("plan_tree");
   const int nn = h->n_nodes, r = h->r;
   h->want_predict = want_predict != 0;
   drop_graph(h);
+  wait_lists(h);
+  tr.mark("wait for build_lists");
   h->nodes.assign(nn, NodeDev{});
-  long long s_off = 0, di_off = 0, ut_off = 0, qt_off = 0, a_off = 0, gt_off = 0, lp_off = 0, vk_off = 0,
-            linv_off = 0, utt_off = 0;
-  h->max_leaf_obs = h->max_leaf_rows = h->max_leaf_unobs = 0;
-  h->max_leaf_W = 1;
-  // kernel-family ids of the work accounting, resolved once (the node loop below makes ~15 updates per node)
+  long long a_off = 0, gt_off = 0, lp_off = 0, vk_off = 0, linv_off = 0;
   const int W_assemble_A = kid(h, "assemble_A");
-  const int W_fold = kid(h, "fold");
   const int W_knot_chol = kid(h, "knot_chol");
   const int W_knot_gram = kid(h, "knot_gram");
   const int W_knot_vkl = kid(h, "knot_vkl");
+  const int W_node_chol = kid(h, "node_chol");
+  const int W_node_gt = kid(h, "node_gt");
+  const int W_predict_fused = kid(h, "predict_fused");
+  const int W_prior_tiles = kid(h, "prior_tiles");
+  const int W_unpermute = kid(h, "unpermute");
+  for (auto& f : h->kflops) f = 0.0;
+  for (auto& f : h->kbytes) f = 0.0;
+  std::vector<double> my_rows_prior((size_t)nn, 0.0), my_rows_pred((size_t)nn, 0.0);
+  for (size_t m = 0; m < h->ptiles_at.size(); ++m)
+    for (size_t i = 0; i < h->ptiles_at[m].size(); ++i) {
+      const int4& t = h->ptiles_at[m][i];
+      my_rows_prior[t.x] += t.z;
+      if (t.w == 0) my_rows_pred[t.x] += t.z;
+    }
+  for (int n = 0; n < nn; ++n) {
+    NodeDev& d = h->nodes[n];
+    d.level = h->level[n];
+    d.kind = h->kind[n];
+    d.parent = h->parent[n];
+    d.child_start = h->child_start[n];
+    d.child_count = h->child_count[n];
+    d.row_start = (int)h->row_start[n];
+    d.row_count = (int)h->row_count[n];
+    d.knot_off = (int)h->knot_off[n];
+    d.W = d.level * r + 1;
+    if (!h->role[n]) continue;       // another rank's subtree
+    if (d.kind != KIND_INTERNAL) continue;
+    const double Kv = (double)d.level * r;
+    const int Wa = (d.level + 1) * r + 1;
+    d.lda = (Wa + 3) / 4 * 4;
+    d.a_off = a_off;
+    a_off += (long long)Wa * d.lda;
+    d.gt_off = gt_off;
+    gt_off += (long long)d.W * r;
+    d.lpinv_off = lp_off;
+    lp_off += (long long)r * r;
+    d.linv_off = linv_off;
+    linv_off += (long long)r * r;
+    d.vk_off = vk_off;
+    vk_off += (long long)r * d.level * r;
+    // rows of this node this rank really works on: all of them unless the node is a replicated top node of a
+    // sharded handle, whose tile list holds only this rank's pieces (+ gathered knot rows, prior pass only)
+    const double nr = my_rows_prior[n], nrp = my_rows_pred[n], rr = (double)r;
+    const double Waf = Kv + rr + 1;
+    add_w(h, W_knot_gram, rr * rr * Kv, 8.0 * (2.0 * rr * Kv + rr * rr / 2));
+    add_w(h, W_knot_chol, 2.0 * rr * rr * rr / 3.0, 8.0 * rr * rr);
+    add_w(h, W_knot_vkl, 2.0 * rr * rr * Kv, 8.0 * (2.0 * rr * Kv + rr * rr));
+    add_w(h, W_prior_tiles, 2.0 * nr * rr * Kv + nr * rr * rr, 8.0 * nr * (Kv + rr + 2));
+    double fa = 0;     // assemble: symmetric half of W x W, K = n_obs (leaf child) or r (internal child)
+    for (int ch = d.child_start; ch < d.child_start + d.child_count; ++ch)
+      if (h->kind[ch] == KIND_INTERNAL && !(h->shard_level > 0 && d.level == h->shard_level - 1)) fa += Waf * Waf * rr;
+    add_w(h, W_assemble_A, fa, 8.0 * Waf * Waf);
+    add_w(h, W_node_chol, 2.0 * rr * rr * rr / 3.0, 8.0 * 2.0 * rr * rr);
+    add_w(h, W_node_gt, (Kv + 1) * rr * rr, 8.0 * (rr * rr + 2 * (Kv + 1) * rr));
+    add_w(h, W_predict_fused, nrp * rr * rr + 2.0 * nrp * rr * Kv + 4.0 * nrp * rr, 8.0 * nrp * rr);
+  }
+  add_w(h, W_unpermute, 0.0, 8.0 * 4.0 * (double)h->N);
+  tr.mark("node loop (tree)");
+  // ---- arena layout, part A
+  Arena ar;
+  Layout& L = h->lay;
+  L = Layout{};
+  const size_t N = (size_t)h->N, D = sizeof(double);
+  L.nodes = ar.take(sizeof(NodeDev) * nn);
+  L.knot_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->knot_rows.size()));
+  L.perm = ar.take(sizeof(int) * N);
+  L.xs = ar.take(D * N);
+  L.ys = ar.take(D * N);
+  L.yobs = ar.take(D * N);
+  L.V = ar.take(D * N * (size_t)h->ldv);
+  L.GTF = ar.take(D * std::max<long long>(1, h->want_predict ? gt_off : 0));
+  L.A = ar.take(D * std::max<long long>(1, a_off));
+  L.GT = ar.take(D * std::max<long long>(1, gt_off));
+  L.LPINV = ar.take(D * std::max<long long>(1, lp_off));
+  L.VK = ar.take(D * std::max<long long>(1, vk_off));
+  L.VKL = ar.take(D * std::max<long long>(1, vk_off));
+  L.LINV = ar.take(D * std::max<long long>(1, linv_off));
+  L.dnode = ar.take(D * nn);
+  L.mean = ar.take(D * N);
+  L.var = ar.take(D * N);
+  L.vnorm = ar.take(D * N);
+  L.xidx = ar.take(D * N);
+  L.status = ar.take(256);
+  L.params = ar.take(256);
+  L.out = ar.take(256);
+  L.stage_locs = ar.take(D * N * h->dim);
+  L.stage_obs = ar.take(D * N);
+  L.out_mean = ar.take(D * N);
+  L.out_sd = ar.take(D * N);
+  h->list_off.assign(h->internal_at.size(), 0);
+  h->ptiles_off.assign(h->internal_at.size(), 0);
+  size_t lo = 0, po = 0;
+  for (size_t m = 0; m < h->internal_at.size(); ++m) {
+    h->list_off[m] = lo;
+    lo += (sizeof(int) * h->internal_at[m].size() + 255) & ~size_t(255);
+    h->ptiles_off[m] = po;
+    po += (sizeof(int4) * h->ptiles_at[m].size() + 255) & ~size_t(255);
+  }
+  h->pgroups_off.assign(h->internal_at.size(), 0);
+  size_t go = 0;
+  for (size_t m = 0; m < h->internal_at.size(); ++m) {
+    h->pgroups_off[m] = go;
+    go += (sizeof(int4) * h->pgroups_at[m].size() + 255) & ~size_t(255);
+  }
+  h->leaves_off = lo;
+  lo += (sizeof(int) * h->leaves.size() + 255) & ~size_t(255);
+  h->sroots_off = lo;
+  lo += (sizeof(int) * h->sroots.size() + 255) & ~size_t(255);
+  L.lists = ar.take(std::max<size_t>(256, lo));
+  L.ptiles = ar.take(std::max<size_t>(256, po));
+  L.pgroups = ar.take(std::max<size_t>(256, go));
+  L.gather = ar.take(std::max<size_t>(256, sizeof(int) * h->gather_rows.size()));
+  L.chunks = ar.take(std::max<size_t>(256, sizeof(int2) * h->emit_chunks.size()));
+  L.ltiles = ar.take(std::max<size_t>(256, sizeof(int4) * h->leaf_tiles.size()));
+  h->total_A = ar.off;
+  h->total_B = 0;
+  h->tree_planned = true;
+  h->planned = h->bound = h->tree_bound = h->uploaded = h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+// Part B.  Offsets are laid out relative to the start of part B; place_obs_part() turns them into offsets from h->ws.
+int plan_obs_impl(mra_handle* h, const double* obs) {
+  HostTrace tr("plan_obs");
+  const int nn = h->n_nodes, r = h->r;
+  long long s_off = 0, di_off = 0, ut_off = 0, qt_off = 0, utt_off = 0;
+  h->max_leaf_obs = h->max_leaf_rows = h->max_leaf_unobs = 0;
+  h->max_leaf_W = 1;
+  const int W_assemble_A = kid(h, "assemble_A");
+  const int W_fold = kid(h, "fold");
   const int W_leaf_chol = kid(h, "leaf_chol");
   const int W_leaf_gram = kid(h, "leaf_gram");
   const int W_leaf_gram_T = kid(h, "leaf_gram_T");
@@ -1099,13 +1243,7 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
   const int W_leaf_trsm = kid(h, "leaf_trsm");
   const int W_leaf_upd = kid(h, "leaf_upd");
   const int W_leaf_ut = kid(h, "leaf_ut");
-  const int W_node_chol = kid(h, "node_chol");
-  const int W_node_gt = kid(h, "node_gt");
   const int W_predict_fused = kid(h, "predict_fused");
-  const int W_prior_tiles = kid(h, "prior_tiles");
-  const int W_unpermute = kid(h, "unpermute");
-  for (auto& f : h->kflops) f = 0.0;
-  for (auto& f : h->kbytes) f = 0.0;
   std::vector<uint8_t, NoInit<uint8_t>> finite_row((size_t)h->N);     // np.isfinite(obs) in tree order (MRANode.py:415)
   {
     // two passes: the flags in the caller's order (a sequential scan of obs), then a gather of BYTES through the
@@ -1188,118 +1326,70 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
     });
   }
   tr.mark("leaf row lists");
-  wait_lists(h);
-  tr.mark("wait for build_lists");
-  std::vector<double> my_rows_prior((size_t)nn, 0.0), my_rows_pred((size_t)nn, 0.0);
-  for (size_t m = 0; m < h->ptiles_at.size(); ++m)
-    for (size_t i = 0; i < h->ptiles_at[m].size(); ++i) {
-      const int4& t = h->ptiles_at[m][i];
-      my_rows_prior[t.x] += t.z;
-      if (t.w == 0) my_rows_pred[t.x] += t.z;
-    }
   int64_t leaf_cursor = 0;
   for (int n = 0; n < nn; ++n) {
     NodeDev& d = h->nodes[n];
-    d.level = h->level[n];
-    d.kind = h->kind[n];
-    d.parent = h->parent[n];
-    d.child_start = h->child_start[n];
-    d.child_count = h->child_count[n];
-    d.row_start = (int)h->row_start[n];
-    d.row_count = (int)h->row_count[n];
-    d.knot_off = (int)h->knot_off[n];
-    d.W = d.level * r + 1;
-    if (!h->role[n]) continue;       // another rank's subtree
+    if (!h->role[n] || d.kind == KIND_INTERNAL) continue;
     const double Kv = (double)d.level * r;
-    if (d.kind == KIND_INTERNAL) {
-      const int Wa = (d.level + 1) * r + 1;
-      d.lda = (Wa + 3) / 4 * 4;
-      d.a_off = a_off;
-      a_off += (long long)Wa * d.lda;
-      d.gt_off = gt_off;
-      gt_off += (long long)d.W * r;
-      d.lpinv_off = lp_off;
-      lp_off += (long long)r * r;
-      d.linv_off = linv_off;
-      linv_off += (long long)r * r;
-      d.vk_off = vk_off;
-      vk_off += (long long)r * d.level * r;
-      // rows of this node this rank really works on: all of them unless the node is a replicated top node of a
-      // sharded handle, whose tile list holds only this rank's pieces (+ gathered knot rows, prior pass only)
-      const double nr = my_rows_prior[n], nrp = my_rows_pred[n], rr = (double)r;
-      const double Waf = Kv + rr + 1;
-      add_w(h, W_knot_gram, rr * rr * Kv, 8.0 * (2.0 * rr * Kv + rr * rr / 2));
-      add_w(h, W_knot_chol, 2.0 * rr * rr * rr / 3.0, 8.0 * rr * rr);
-      add_w(h, W_knot_vkl, 2.0 * rr * rr * Kv, 8.0 * (2.0 * rr * Kv + rr * rr));
-      add_w(h, W_prior_tiles, 2.0 * nr * rr * Kv + nr * rr * rr, 8.0 * nr * (Kv + rr + 2));
-      double fa = 0;     // assemble: symmetric half of W x W, K = n_obs (leaf child) or r (internal child)
-      for (int ch = d.child_start; ch < d.child_start + d.child_count; ++ch)
-        if (h->kind[ch] == KIND_INTERNAL && !(h->shard_level > 0 && d.level == h->shard_level - 1)) fa += Waf * Waf * rr;
-      add_w(h, W_assemble_A, fa, 8.0 * Waf * Waf);
-      add_w(h, W_node_chol, 2.0 * rr * rr * rr / 3.0, 8.0 * 2.0 * rr * rr);
-      add_w(h, W_node_gt, (Kv + 1) * rr * rr, 8.0 * (rr * rr + 2 * (Kv + 1) * rr));
-      add_w(h, W_predict_fused, nrp * rr * rr + 2.0 * nrp * rr * Kv + 4.0 * nrp * rr, 8.0 * nrp * rr);
-    } else {
-      if (d.kind == KIND_LEAF) {
-        d.obs_off = leaf_obs_off[leaf_cursor];
-        d.unobs_off = leaf_unobs_off[leaf_cursor];
-        d.n_obs = leaf_obs_off[leaf_cursor + 1] - d.obs_off;
-        d.n_unobs = leaf_unobs_off[leaf_cursor + 1] - d.unobs_off;
-        ++leaf_cursor;
-      } else {          // orphan rows: no data, no residual term
-        d.obs_off = d.unobs_off = 0;
-        d.n_obs = d.n_unobs = 0;
-      }
-      if (d.n_obs > 0) h->max_leaf_unobs = std::max(h->max_leaf_unobs, d.n_unobs);
-      d.ldo = std::max(4, (d.n_obs + 3) / 4 * 4);
-      const int nb = (d.n_obs + TB - 1) / TB;
-      d.s_off = s_off;
-      s_off += (long long)d.n_obs * d.ldo;
-      d.di_off = di_off;
-      di_off += (long long)nb * TB * TB;
-      d.ut_off = ut_off;
-      ut_off += (long long)d.W * d.ldo;
-      d.utt_off = utt_off;
-      utt_off += (long long)d.n_obs * std::max(2, (d.W - 1 + 1) / 2 * 2);
-      d.qt_off = qt_off;
-      if (h->want_predict) qt_off += (long long)d.row_count * d.ldo;
-      h->max_leaf_obs = std::max(h->max_leaf_obs, d.n_obs);
-      h->max_leaf_rows = std::max(h->max_leaf_rows, d.row_count);
-      if (d.n_obs > 0) h->max_leaf_W = std::max(h->max_leaf_W, d.W);
-      const double no = d.n_obs, nl = d.row_count, W = Kv + 1;
-      add_w(h, W_leaf_gram, no * no * Kv, 8.0 * (no * Kv + no * no / 2));
-      for (int pb = 0; pb * TB < d.n_obs; ++pb) {      // blocked factorisation as executed (triangular halves)
-        const double nv = std::min(TB, d.n_obs - pb * TB), Kp = (double)pb * TB, below = no - Kp - nv;
-        add_w(h, W_leaf_chol, 2.0 * nv * nv * nv / 3.0, 8.0 * 2.0 * nv * nv);
-        if (pb > 0) add_w(h, W_leaf_upd, nv * nv * Kp, 8.0 * (nv * Kp + nv * nv));
-        if (below > 0) add_w(h, W_leaf_trsm, below * nv * (2.0 * Kp + nv), 8.0 * (below * (Kp + 2 * nv) + nv * Kp + nv * nv));
-      }
-      if (h->leaf_v2) {
-        for (int bj = 0; (bj + 1) * TB < d.n_obs; ++bj)
-          for (int bi = bj + 1; bi * TB < d.n_obs; ++bi) {
-            const double nvi = std::min(TB, d.n_obs - bi * TB);
-            add_w(h, W_leaf_linv, nvi * TB * TB * (bi - bj) + nvi * nvi * TB, 8.0 * (3.0 * nvi * TB + TB * TB * (bi - bj)));
-          }
-        add_w(h, W_leaf_linv, 0.0, 8.0 * no * no);
-        add_w(h, W_leaf_ut, no * no * Kv, 8.0 * (3 * no * Kv + no * no / 2));
-      } else {
-        add_w(h, W_leaf_solve, no * no * W, 8.0 * (2 * no * W + no * no / 2));
-      }
-      add_w(h, W_assemble_A, W * W * no, 8.0 * no * W);
-      if (d.kind == KIND_LEAF) {
-        add_w(h, W_predict_fused, 2.0 * nl * Kv, 8.0 * nl * (Kv + 2));
-        if (h->leaf_v2) {
-          add_w(h, W_leaf_q, 2.0 * (nl - no) * no * Kv + (nl - no) * no * no, 8.0 * ((nl - no) * (Kv + no) + no * (Kv + no / 2)));
-          add_w(h, W_leaf_qobs, 0.0, 8.0 * 2.0 * no * no);
-        } else {
-          add_w(h, W_leaf_gram_T, 2.0 * (nl - no) * no * Kv, 8.0 * ((nl + no) * Kv + nl * no));
-          add_w(h, W_leaf_solve_Q, nl * no * no, 8.0 * (2 * nl * no + no * no / 2));
+    if (d.kind == KIND_LEAF) {
+      d.obs_off = leaf_obs_off[leaf_cursor];
+      d.unobs_off = leaf_unobs_off[leaf_cursor];
+      d.n_obs = leaf_obs_off[leaf_cursor + 1] - d.obs_off;
+      d.n_unobs = leaf_unobs_off[leaf_cursor + 1] - d.unobs_off;
+      ++leaf_cursor;
+    } else {          // orphan rows: no data, no residual term
+      d.obs_off = d.unobs_off = 0;
+      d.n_obs = d.n_unobs = 0;
+    }
+    if (d.n_obs > 0) h->max_leaf_unobs = std::max(h->max_leaf_unobs, d.n_unobs);
+    d.ldo = std::max(4, (d.n_obs + 3) / 4 * 4);
+    const int nb = (d.n_obs + TB - 1) / TB;
+    d.s_off = s_off;
+    s_off += (long long)d.n_obs * d.ldo;
+    d.di_off = di_off;
+    di_off += (long long)nb * TB * TB;
+    d.ut_off = ut_off;
+    ut_off += (long long)d.W * d.ldo;
+    d.utt_off = utt_off;
+    utt_off += (long long)d.n_obs * std::max(2, (d.W - 1 + 1) / 2 * 2);
+    d.qt_off = qt_off;
+    if (h->want_predict) qt_off += (long long)d.row_count * d.ldo;
+    h->max_leaf_obs = std::max(h->max_leaf_obs, d.n_obs);
+    h->max_leaf_rows = std::max(h->max_leaf_rows, d.row_count);
+    if (d.n_obs > 0) h->max_leaf_W = std::max(h->max_leaf_W, d.W);
+    const double no = d.n_obs, nl = d.row_count, W = Kv + 1;
+    add_w(h, W_leaf_gram, no * no * Kv, 8.0 * (no * Kv + no * no / 2));
+    for (int pb = 0; pb * TB < d.n_obs; ++pb) {      // blocked factorisation as executed (triangular halves)
+      const double nv = std::min(TB, d.n_obs - pb * TB), Kp = (double)pb * TB, below = no - Kp - nv;
+      add_w(h, W_leaf_chol, 2.0 * nv * nv * nv / 3.0, 8.0 * 2.0 * nv * nv);
+      if (pb > 0) add_w(h, W_leaf_upd, nv * nv * Kp, 8.0 * (nv * Kp + nv * nv));
+      if (below > 0) add_w(h, W_leaf_trsm, below * nv * (2.0 * Kp + nv), 8.0 * (below * (Kp + 2 * nv) + nv * Kp + nv * nv));
+    }
+    if (h->leaf_v2) {
+      for (int bj = 0; (bj + 1) * TB < d.n_obs; ++bj)
+        for (int bi = bj + 1; bi * TB < d.n_obs; ++bi) {
+          const double nvi = std::min(TB, d.n_obs - bi * TB);
+          add_w(h, W_leaf_linv, nvi * TB * TB * (bi - bj) + nvi * nvi * TB, 8.0 * (3.0 * nvi * TB + TB * TB * (bi - bj)));
         }
-        add_w(h, W_predict_fused, 2.0 * nl * no * W + 2.0 * nl * no, 8.0 * (nl * no + no * W));
+      add_w(h, W_leaf_linv, 0.0, 8.0 * no * no);
+      add_w(h, W_leaf_ut, no * no * Kv, 8.0 * (3 * no * Kv + no * no / 2));
+    } else {
+      add_w(h, W_leaf_solve, no * no * W, 8.0 * (2 * no * W + no * no / 2));
+    }
+    add_w(h, W_assemble_A, W * W * no, 8.0 * no * W);
+    if (d.kind == KIND_LEAF) {
+      add_w(h, W_predict_fused, 2.0 * nl * Kv, 8.0 * nl * (Kv + 2));
+      if (h->leaf_v2) {
+        add_w(h, W_leaf_q, 2.0 * (nl - no) * no * Kv + (nl - no) * no * no, 8.0 * ((nl - no) * (Kv + no) + no * (Kv + no / 2)));
+        add_w(h, W_leaf_qobs, 0.0, 8.0 * 2.0 * no * no);
+      } else {
+        add_w(h, W_leaf_gram_T, 2.0 * (nl - no) * no * Kv, 8.0 * ((nl + no) * Kv + nl * no));
+        add_w(h, W_leaf_solve_Q, nl * no * no, 8.0 * (2 * nl * no + no * no / 2));
       }
+      add_w(h, W_predict_fused, 2.0 * nl * no * W + 2.0 * nl * no, 8.0 * (nl * no + no * W));
     }
   }
-  tr.mark("node loop");
+  tr.mark("node loop (leaves)");
   h->n_obs_total = (int64_t)h->obs_rows.size();
   h->fold_items.clear();
   if (h->want_predict) {
@@ -1318,7 +1408,6 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
       add_w(h, W_fold, 2.0 * d.level * (double)r * r * cols, 8.0 * 2.0 * d.level * r * cols);
     }
   }
-  add_w(h, W_unpermute, 0.0, 8.0 * 4.0 * (double)h->N);
   h->flops_lik = h->flops_pred = 0.0;
   for (size_t i = 0; i < h->kname.size(); ++i) {
     const std::string& nm = h->kname[i];
@@ -1327,75 +1416,76 @@ int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspa
     (pred ? h->flops_pred : h->flops_lik) += h->kflops[i];
   }
   tr.mark("fold items");
-  // ---- arena layout
+  // ---- arena layout, part B (offsets relative to its start)
   Arena ar;
+  Layout& R = h->lay_b;
+  R = Layout{};
+  const size_t D = sizeof(double);
+  R.obs_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->obs_rows.size()));
+  R.unobs_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->unobs_rows.size()));
+  R.S = ar.take(D * std::max<long long>(1, s_off));
+  R.LS = ar.take(D * std::max<long long>(1, h->leaf_v2 ? s_off : 0));
+  R.UTTN = ar.take(D * std::max<long long>(1, h->leaf_v2 ? utt_off : 0));
+  R.DI = ar.take(D * std::max<long long>(1, di_off));
+  R.UT = ar.take(D * std::max<long long>(1, ut_off));
+  R.QT = ar.take(D * std::max<long long>(1, qt_off));
+  R.UTF = ar.take(D * std::max<long long>(1, h->want_predict ? ut_off : 0));
+  R.fold = ar.take(std::max<size_t>(256, sizeof(int4) * h->fold_items.size()));
+  h->total_B = ar.off;
+  return MRA_OK;
+}
+
+// part B starts `delta` bytes after h->ws (modulo 2^64 when it lives in an allocation of its own)
+void place_obs_part(mra_handle* h, size_t delta) {
   Layout& L = h->lay;
-  const size_t N = (size_t)h->N, D = sizeof(double);
-  L.nodes = ar.take(sizeof(NodeDev) * nn);
-  L.knot_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->knot_rows.size()));
-  L.obs_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->obs_rows.size()));
-  L.unobs_rows = ar.take(sizeof(int) * std::max<size_t>(1, h->unobs_rows.size()));
-  L.perm = ar.take(sizeof(int) * N);
-  L.xs = ar.take(D * N);
-  L.ys = ar.take(D * N);
-  L.yobs = ar.take(D * N);
-  L.V = ar.take(D * N * (size_t)h->ldv);
-  L.S = ar.take(D * std::max<long long>(1, s_off));
-  L.LS = ar.take(D * std::max<long long>(1, h->leaf_v2 ? s_off : 0));
-  L.UTTN = ar.take(D * std::max<long long>(1, h->leaf_v2 ? utt_off : 0));
-  L.DI = ar.take(D * std::max<long long>(1, di_off));
-  L.UT = ar.take(D * std::max<long long>(1, ut_off));
-  L.QT = ar.take(D * std::max<long long>(1, qt_off));
-  L.UTF = ar.take(D * std::max<long long>(1, h->want_predict ? ut_off : 0));
-  L.GTF = ar.take(D * std::max<long long>(1, h->want_predict ? gt_off : 0));
-  L.A = ar.take(D * std::max<long long>(1, a_off));
-  L.GT = ar.take(D * std::max<long long>(1, gt_off));
-  L.LPINV = ar.take(D * std::max<long long>(1, lp_off));
-  L.VK = ar.take(D * std::max<long long>(1, vk_off));
-  L.VKL = ar.take(D * std::max<long long>(1, vk_off));
-  L.LINV = ar.take(D * std::max<long long>(1, linv_off));
-  L.dnode = ar.take(D * nn);
-  L.mean = ar.take(D * N);
-  L.var = ar.take(D * N);
-  L.vnorm = ar.take(D * N);
-  L.xidx = ar.take(D * N);
-  L.status = ar.take(256);
-  L.params = ar.take(256);
-  L.out = ar.take(256);
-  L.stage_locs = ar.take(D * N * h->dim);
-  L.stage_obs = ar.take(D * N);
-  L.out_mean = ar.take(D * N);
-  L.out_sd = ar.take(D * N);
-  h->list_off.assign(h->internal_at.size(), 0);
-  h->ptiles_off.assign(h->internal_at.size(), 0);
-  size_t lo = 0, po = 0;
-  for (size_t m = 0; m < h->internal_at.size(); ++m) {
-    h->list_off[m] = lo;
-    lo += (sizeof(int) * h->internal_at[m].size() + 255) & ~size_t(255);
-    h->ptiles_off[m] = po;
-    po += (sizeof(int4) * h->ptiles_at[m].size() + 255) & ~size_t(255);
-  }
-  h->pgroups_off.assign(h->internal_at.size(), 0);
-  size_t go = 0;
-  for (size_t m = 0; m < h->internal_at.size(); ++m) {
-    h->pgroups_off[m] = go;
-    go += (sizeof(int4) * h->pgroups_at[m].size() + 255) & ~size_t(255);
-  }
-  h->leaves_off = lo;
-  lo += (sizeof(int) * h->leaves.size() + 255) & ~size_t(255);
-  h->sroots_off = lo;
-  lo += (sizeof(int) * h->sroots.size() + 255) & ~size_t(255);
-  L.lists = ar.take(std::max<size_t>(256, lo));
-  L.ptiles = ar.take(std::max<size_t>(256, po));
-  L.pgroups = ar.take(std::max<size_t>(256, go));
-  L.gather = ar.take(std::max<size_t>(256, sizeof(int) * h->gather_rows.size()));
-  L.chunks = ar.take(std::max<size_t>(256, sizeof(int2) * h->emit_chunks.size()));
-  L.ltiles = ar.take(std::max<size_t>(256, sizeof(int4) * h->leaf_tiles.size()));
-  L.fold = ar.take(std::max<size_t>(256, sizeof(int4) * h->fold_items.size()));
-  L.total = ar.off;
-  *workspace_bytes = L.total;
+  const Layout& R = h->lay_b;
+  L.obs_rows = delta + R.obs_rows;
+  L.unobs_rows = delta + R.unobs_rows;
+  L.S = delta + R.S;
+  L.LS = delta + R.LS;
+  L.UTTN = delta + R.UTTN;
+  L.DI = delta + R.DI;
+  L.UT = delta + R.UT;
+  L.QT = delta + R.QT;
+  L.UTF = delta + R.UTF;
+  L.fold = delta + R.fold;
+}
+
+}  // namespace
+
+int mra_plan(mra_handle* h, const double* obs, int want_predict, size_t* workspace_bytes) {
+  if (!h || !obs || !workspace_bytes) return MRA_ERR_ARG;
+  if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
+  int rc = plan_tree_impl(h, want_predict);
+  if (rc) return rc;
+  rc = plan_obs_impl(h, obs);
+  if (rc) return rc;
+  place_obs_part(h, h->total_A);
+  h->lay.total = h->total_A + h->total_B;
+  *workspace_bytes = h->lay.total;
   h->planned = true;
+  h->split_arena = false;
   h->bound = h->uploaded = h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+int mra_plan_tree(mra_handle* h, int want_predict, size_t* tree_bytes) {
+  if (!h || !tree_bytes) return MRA_ERR_ARG;
+  if (!h->has_structure) return fail(h, MRA_ERR_STATE, "mra_set_structure must be called first");
+  if (h->shard_level > 0) return fail(h, MRA_ERR_STATE, "the two-part plan is for unsharded handles");
+  int rc = plan_tree_impl(h, want_predict);
+  if (rc) return rc;
+  *tree_bytes = h->total_A;
+  return MRA_OK;
+}
+
+int mra_plan_obs(mra_handle* h, const double* obs, size_t* obs_bytes) {
+  if (!h || !obs || !obs_bytes) return MRA_ERR_ARG;
+  if (!h->tree_planned) return fail(h, MRA_ERR_STATE, "mra_plan_tree must be called first");
+  int rc = plan_obs_impl(h, obs);
+  if (rc) return rc;
+  *obs_bytes = h->total_B;
+  h->planned = true;
   return MRA_OK;
 }
 
@@ -1415,22 +1505,12 @@ int mra_bind_workspace(mra_handle* h, void* dev_workspace, size_t bytes) {
   return MRA_OK;
 }
 
-// structure tables + inputs; the inputs come from host buffers (locs, obs) or are already on the device (dev_*)
-static int upload_impl(mra_handle* h, const double* locs, const double* obs, const double* dev_locs,
-                       const double* dev_obs, void* stream) {
-  if (!h->bound) return fail(h, MRA_ERR_STATE, "mra_bind_workspace must be called first");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// tree-dependent tables (part A of the arena)
+static int upload_tree_tables(mra_handle* h, cudaStream_t st) {
   const Layout& L = h->lay;
   const size_t N = (size_t)h->N;
-  DEVICE_SCOPE(h);
-  CU(cudaMemcpyAsync(h->ws + L.nodes, h->nodes.data(), sizeof(NodeDev) * h->nodes.size(), cudaMemcpyHostToDevice, st));
   if (!h->knot_rows.empty())
     CU(cudaMemcpyAsync(h->ws + L.knot_rows, h->knot_rows.data(), sizeof(int) * h->knot_rows.size(), cudaMemcpyHostToDevice, st));
-  if (!h->obs_rows.empty())
-    CU(cudaMemcpyAsync(h->ws + L.obs_rows, h->obs_rows.data(), sizeof(int) * h->obs_rows.size(), cudaMemcpyHostToDevice, st));
-  if (!h->unobs_rows.empty())
-    CU(cudaMemcpyAsync(h->ws + L.unobs_rows, h->unobs_rows.data(), sizeof(int) * h->unobs_rows.size(),
-                       cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(h->ws + L.perm, h->perm.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
   for (size_t m = 0; m < h->internal_at.size(); ++m) {
     if (!h->internal_at[m].empty())
@@ -1457,15 +1537,35 @@ static int upload_impl(mra_handle* h, const double* locs, const double* obs, con
   if (!h->leaf_tiles.empty())
     CU(cudaMemcpyAsync(h->ws + L.ltiles, h->leaf_tiles.data(), sizeof(int4) * h->leaf_tiles.size(),
                        cudaMemcpyHostToDevice, st));
-  if (!h->fold_items.empty())
-    CU(cudaMemcpyAsync(h->ws + L.fold, h->fold_items.data(), sizeof(int4) * h->fold_items.size(),
-                       cudaMemcpyHostToDevice, st));
   if (!h->emit_chunks.empty())
     CU(cudaMemcpyAsync(h->ws + L.chunks, h->emit_chunks.data(), sizeof(int2) * h->emit_chunks.size(),
                        cudaMemcpyHostToDevice, st));
   if (!h->leaves.empty())
     CU(cudaMemcpyAsync(h->ws + L.lists + h->leaves_off, h->leaves.data(), sizeof(int) * h->leaves.size(),
                        cudaMemcpyHostToDevice, st));
+  return MRA_OK;
+}
+
+// node table + observation-dependent tables (part B; the node table carries the leaves' offsets into it)
+static int upload_obs_tables(mra_handle* h, cudaStream_t st) {
+  const Layout& L = h->lay;
+  CU(cudaMemcpyAsync(h->ws + L.nodes, h->nodes.data(), sizeof(NodeDev) * h->nodes.size(), cudaMemcpyHostToDevice, st));
+  if (!h->obs_rows.empty())
+    CU(cudaMemcpyAsync(h->ws + L.obs_rows, h->obs_rows.data(), sizeof(int) * h->obs_rows.size(), cudaMemcpyHostToDevice, st));
+  if (!h->unobs_rows.empty())
+    CU(cudaMemcpyAsync(h->ws + L.unobs_rows, h->unobs_rows.data(), sizeof(int) * h->unobs_rows.size(),
+                       cudaMemcpyHostToDevice, st));
+  if (!h->fold_items.empty())
+    CU(cudaMemcpyAsync(h->ws + L.fold, h->fold_items.data(), sizeof(int4) * h->fold_items.size(),
+                       cudaMemcpyHostToDevice, st));
+  return MRA_OK;
+}
+
+// inputs into tree order; they come from host buffers (locs, obs) or are already on the device (dev_*)
+static int permute_inputs(mra_handle* h, const double* locs, const double* obs, const double* dev_locs,
+                          const double* dev_obs, cudaStream_t st) {
+  const Layout& L = h->lay;
+  const size_t N = (size_t)h->N;
   if (!dev_locs) {
     CU(cudaMemcpyAsync(h->ws + L.stage_locs, locs, sizeof(double) * N * h->dim, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->ws + L.stage_obs, obs, sizeof(double) * N, cudaMemcpyHostToDevice, st));
@@ -1476,9 +1576,79 @@ static int upload_impl(mra_handle* h, const double* locs, const double* obs, con
       dev_locs, dev_obs, at<int>(h, L.perm), (int)N, h->dim,
       at<double>(h, L.xs), at<double>(h, L.ys), at<double>(h, L.yobs), at<double>(h, L.xidx));
   CU(cudaGetLastError());
+  return MRA_OK;
+}
+
+static int upload_impl(mra_handle* h, const double* locs, const double* obs, const double* dev_locs,
+                       const double* dev_obs, void* stream) {
+  if (!h->bound) return fail(h, MRA_ERR_STATE, "mra_bind_workspace must be called first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DEVICE_SCOPE(h);
+  int rc = upload_obs_tables(h, st);
+  if (rc) return rc;
+  rc = upload_tree_tables(h, st);
+  if (rc) return rc;
+  rc = permute_inputs(h, locs, obs, dev_locs, dev_obs, st);
+  if (rc) return rc;
   CU(cudaStreamSynchronize(st));   // host vectors may change after return
   h->uploaded = true;
   h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+// Two-part set-up (see mra_plan_tree): part A of the arena + the tree tables + the inputs; after it the prior pass may run
+// (mra_set_cov / mra_set_nugget, mra_stream_begin_async, mra_stream_part_prior_async).
+int mra_bind_tree(mra_handle* h, void* dev_workspace, size_t bytes, const double* dev_locs, const double* dev_obs,
+                  void* stream) {
+  if (!h || !dev_workspace || !dev_locs || !dev_obs) return MRA_ERR_ARG;
+  if (!h->tree_planned) return fail(h, MRA_ERR_STATE, "mra_plan_tree must be called first");
+  if (bytes < h->total_A) return fail(h, MRA_ERR_NOMEM, "workspace smaller than mra_plan_tree reported");
+  if (reinterpret_cast<uintptr_t>(dev_workspace) % 256) return fail(h, MRA_ERR_ARG, "workspace must be 256-byte aligned");
+  DEVICE_SCOPE(h);
+  drop_graph(h);
+  h->ws = static_cast<char*>(dev_workspace);
+  h->ws_bytes = bytes;
+  h->split_arena = true;
+  int rc = configure_kernels(h);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the node table as far as the prior pass reads it (the leaves' fields follow with mra_bind_obs)
+  CU(cudaMemcpyAsync(h->ws + h->lay.nodes, h->nodes.data(), sizeof(NodeDev) * h->nodes.size(), cudaMemcpyHostToDevice, st));
+  rc = upload_tree_tables(h, st);
+  if (rc) return rc;
+  rc = permute_inputs(h, nullptr, nullptr, dev_locs, dev_obs, st);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(st));
+  h->tree_bound = true;
+  h->uploaded = true;
+  h->bound = false;
+  h->lik_done = h->pred_done = false;
+  return MRA_OK;
+}
+
+// Part B in an allocation of its own; its tables travel on the handle's copy stream (the prior pass may be running on
+// `stream`, which only waits for them).  The handle is fully set up afterwards.
+int mra_bind_obs(mra_handle* h, void* dev_workspace_obs, size_t bytes, void* stream) {
+  if (!h || !dev_workspace_obs) return MRA_ERR_ARG;
+  if (!h->tree_bound || !h->planned) return fail(h, MRA_ERR_STATE, "mra_bind_tree and mra_plan_obs must be called first");
+  if (bytes < h->total_B) return fail(h, MRA_ERR_NOMEM, "workspace smaller than mra_plan_obs reported");
+  if (reinterpret_cast<uintptr_t>(dev_workspace_obs) % 256) return fail(h, MRA_ERR_ARG, "workspace must be 256-byte aligned");
+  DEVICE_SCOPE(h);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  place_obs_part(h, (size_t)(reinterpret_cast<uintptr_t>(dev_workspace_obs) - reinterpret_cast<uintptr_t>(h->ws)));
+  h->lay.total = h->total_A;
+  int rc = configure_kernels(h);      // the leaf kernels' shared-memory sizes depend on the observation counts
+  if (rc) return rc;
+  if (!h->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->copy_event, cudaEventDisableTiming));
+  }
+  rc = upload_obs_tables(h, h->copy_stream);
+  if (rc) return rc;
+  CU(cudaEventRecord(h->copy_event, h->copy_stream));
+  CU(cudaStreamWaitEvent(st, h->copy_event, 0));
+  CU(cudaStreamSynchronize(h->copy_stream));   // host vectors may change after return
+  h->bound = true;
   return MRA_OK;
 }
 
@@ -1719,17 +1889,12 @@ int mra_stream_begin_async(mra_handle* h, void* stream, const int64_t* knot_rows
   CU(cudaGetLastError());
   h->stream_open = true;
   h->stream_parts_done = 0;
+  h->stream_prior_done = 0;
   return MRA_OK;
 }
 
-int mra_stream_part_async(mra_handle* h, void* stream, int32_t part, const int64_t* knot_rows) {
-  if (!h) return MRA_ERR_ARG;
-  if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
-  if (part < 0 || part >= h->n_parts) return fail(h, MRA_ERR_ARG, "part out of range");
-  if (h->stream_parts_done & (1 << part)) return fail(h, MRA_ERR_STATE, "part already evaluated");
-  if (!(h->my_parts & (1 << part))) return fail(h, MRA_ERR_ARG, "this part belongs to another rank");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DEVICE_SCOPE(h);
+// the prior levels >= 1 of one part (needs part A of the arena only)
+static int stream_part_prior(mra_handle* h, cudaStream_t st, int32_t part, const int64_t* knot_rows) {
   DevCtx c = make_ctx(h);
   int rc = upload_knot_ranges(h, st, knot_rows, h->part_knots[part], h->part_gather[part]);
   if (rc) return rc;
@@ -1742,6 +1907,39 @@ int mra_stream_part_async(mra_handle* h, void* stream, int32_t part, const int64
     rc = prior_level(h, st, c, m, h->part_nodes[m][part], h->part_tiles[m][part]);
     if (rc) return rc;
   }
+  h->stream_prior_done |= 1 << part;
+  return MRA_OK;
+}
+
+int mra_stream_part_prior_async(mra_handle* h, void* stream, int32_t part, const int64_t* knot_rows) {
+  if (!h) return MRA_ERR_ARG;
+  if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
+  if (part < 0 || part >= h->n_parts) return fail(h, MRA_ERR_ARG, "part out of range");
+  if ((h->stream_parts_done | h->stream_prior_done) & (1 << part)) return fail(h, MRA_ERR_STATE, "part already evaluated");
+  if (!(h->my_parts & (1 << part))) return fail(h, MRA_ERR_ARG, "this part belongs to another rank");
+  DEVICE_SCOPE(h);
+  int rc = stream_part_prior(h, static_cast<cudaStream_t>(stream), part, knot_rows);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  return MRA_OK;
+}
+
+int mra_stream_part_async(mra_handle* h, void* stream, int32_t part, const int64_t* knot_rows) {
+  if (!h) return MRA_ERR_ARG;
+  if (!h->stream_open) return fail(h, MRA_ERR_STATE, "mra_stream_begin_async must be called first");
+  if (!h->bound) return fail(h, MRA_ERR_STATE, "the observation part of the plan is not bound yet (mra_bind_obs)");
+  if (part < 0 || part >= h->n_parts) return fail(h, MRA_ERR_ARG, "part out of range");
+  if (h->stream_parts_done & (1 << part)) return fail(h, MRA_ERR_STATE, "part already evaluated");
+  if (!(h->my_parts & (1 << part))) return fail(h, MRA_ERR_ARG, "this part belongs to another rank");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DEVICE_SCOPE(h);
+  int rc = MRA_OK;
+  if (!(h->stream_prior_done & (1 << part))) {
+    rc = stream_part_prior(h, st, part, knot_rows);
+    if (rc) return rc;
+  }
+  DevCtx c = make_ctx(h);
+  const int nl = (int)h->internal_at.size();
   for (const Range& rg : h->part_leaves[part]) {
     rc = leaf_terms(h, st, c, rg);
     if (rc) return rc;

@@ -22,12 +22,15 @@ def _dptr(a):
 
 class DeviceSession(object):
     def __init__(self, structure, locs, obs, want_predict=True, device=None, group=None, emulate=None,
-                 gather="all", staged=None):
+                 gather="all", staged=None, two_part=False):
         """group: a torch.distributed process group (or True for the default group) to shard whole
         subtrees across its ranks, one GPU per rank (pymra_b200/shard.py); None = single GPU.
         emulate=(world, rank): build the shard of `rank` without a process group; the caller drives
         likelihood_local_async / likelihood_top_async and reduces `summary` itself (single-GPU tests).
-        staged=(dev_locs, dev_obs): torch tensors already holding locs / obs on the device (caller's order)."""
+        staged=(dev_locs, dev_obs): torch tensors already holding locs / obs on the device (caller's order).
+        two_part=True (unsharded, needs `staged`): only the tree-dependent half of the set-up runs here (mra_plan_tree /
+        mra_bind_tree), so that the prior pass can be launched at once; finish_plan() does the observation half
+        (mra_plan_obs / mra_bind_obs) while the device is already busy."""
         torch = _torch()
         self.structure = structure
         self.N = structure.N
@@ -35,6 +38,7 @@ class DeviceSession(object):
         self.lib = _ffi.lib()
         self.h = C.c_void_p()
         self.timings = {}
+        self.ws = self.ws_obs = None
         t0 = time.perf_counter()
         st = self.lib.mra_create(C.byref(self.h), self.dev.index)
         if st != 0:
@@ -64,6 +68,21 @@ class DeviceSession(object):
         t0 = time.perf_counter()
         obs_c = np.ascontiguousarray(np.asarray(obs, dtype=np.float64).reshape(self.N))
         locs_c = np.ascontiguousarray(np.asarray(locs, dtype=np.float64).reshape(self.N, structure.d))
+        self._pending_obs = None
+        if two_part and staged is not None and not self.shard_level:
+            nbytes = C.c_size_t()
+            self.check(self.lib.mra_plan_tree(self.h, 1 if want_predict else 0, C.byref(nbytes)))
+            t1 = time.perf_counter()
+            self.ws = torch.empty(int(nbytes.value) + 256, dtype=torch.uint8, device=self.dev)
+            aligned = (self.ws.data_ptr() + 255) // 256 * 256
+            t2 = time.perf_counter()
+            self.check(self.lib.mra_bind_tree(self.h, C.c_void_p(aligned), C.c_size_t(int(nbytes.value)),
+                                              C.c_void_p(staged[0].data_ptr()), C.c_void_p(staged[1].data_ptr()),
+                                              self.stream()))
+            self.workspace_bytes = int(nbytes.value)
+            self._pending_obs = obs_c
+            self.timings.update(plan_tree=t1 - t0, alloc_bind=t2 - t1, upload_tree=time.perf_counter() - t2)
+            return
         nbytes = C.c_size_t()
         self.check(self.lib.mra_plan(self.h, _dptr(obs_c), 1 if want_predict else 0, C.byref(nbytes)))
         t1 = time.perf_counter()
@@ -78,6 +97,22 @@ class DeviceSession(object):
         else:
             self.upload(locs_c, obs_c)
         self.timings.update(plan=t1 - t0, alloc_bind=t2 - t1, upload=time.perf_counter() - t2)
+
+    def finish_plan(self):
+        """Second half of a two_part set-up: NaN scan, the leaves' row lists, the observation-dependent part of the arena."""
+        if self._pending_obs is None:
+            return
+        torch = _torch()
+        t0 = time.perf_counter()
+        nbytes = C.c_size_t()
+        self.check(self.lib.mra_plan_obs(self.h, _dptr(self._pending_obs), C.byref(nbytes)))
+        t1 = time.perf_counter()
+        self.ws_obs = torch.empty(int(nbytes.value) + 256, dtype=torch.uint8, device=self.dev)
+        aligned = (self.ws_obs.data_ptr() + 255) // 256 * 256
+        self.check(self.lib.mra_bind_obs(self.h, C.c_void_p(aligned), C.c_size_t(int(nbytes.value)), self.stream()))
+        self.workspace_bytes += int(nbytes.value)
+        self._pending_obs = None
+        self.timings.update(plan_obs=t1 - t0, upload_obs=time.perf_counter() - t1)
 
     # ---- plumbing
     def check(self, status):
@@ -179,6 +214,10 @@ class DeviceSession(object):
 
     def stream_part(self, part):
         self.check(self.lib.mra_stream_part_async(self.h, self.stream(), int(part), self._knots_ptr()))
+
+    def stream_part_prior(self, part):
+        """Only the prior levels of the part (allowed before finish_plan)."""
+        self.check(self.lib.mra_stream_part_prior_async(self.h, self.stream(), int(part), self._knots_ptr()))
 
     def stream_end_local(self):
         """Sharded at level 1: my summaries into self.summary (the caller reduces them, then likelihood_top_async)."""
@@ -361,6 +400,7 @@ class DeviceSession(object):
             self.lib.mra_destroy(self.h)
             self.h = None
             self.ws = None
+            self.ws_obs = None
 
     def __del__(self):
         try:

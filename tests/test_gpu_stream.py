@@ -30,8 +30,12 @@ def construct(locs, y, r, M, stream, monkeypatch, cov=None, crit=-1):
     return t, float(t.getLikelihood()[0, 0]), np.asarray(mean).ravel().copy(), sd.copy(), state
 
 
-@pytest.mark.parametrize("n_side,r,M,crit", [(300, 16, 3, -1), (300, 16, 4, 1), (700, 32, 5, -1), (2000, 64, 10, -1)])
-def test_streamed_equals_plain(n_side, r, M, crit, monkeypatch):
+@pytest.mark.parametrize("n_side,r,M,crit,two_part", [(300, 16, 3, -1, 1), (300, 16, 4, 1, 1), (700, 32, 5, -1, 1),
+                                                      (700, 32, 5, -1, 0), (2000, 64, 10, -1, 1)])
+def test_streamed_equals_plain(n_side, r, M, crit, two_part, monkeypatch):
+    # two_part: the set-up in two halves (mra_plan_tree / mra_bind_tree, then mra_plan_obs / mra_bind_obs while the prior
+    # pass is already running, the arena in two allocations) against the one-piece set-up
+    monkeypatch.setenv("PYMRA_B200_TWO_PART", str(two_part))
     locs, y = make(n_side)
     tp, lp, mp, sp, statep = construct(locs, y, r, M, False, monkeypatch, crit=crit)
     assert "streamed" not in tp.timings
@@ -39,6 +43,7 @@ def test_streamed_equals_plain(n_side, r, M, crit, monkeypatch):
     del tp
     ts, ls, ms, ss, states = construct(locs, y, r, M, True, monkeypatch, crit=crit)
     assert ts.timings.get("streamed") == 1.0
+    assert ("plan_obs" in ts.timings) == bool(two_part)
     assert np.array_equal(ts._structure.knot_rows, kp)
     assert np.array_equal(statep[1], states[1]) and statep[2] == states[2]
     assert ls == lp
