@@ -529,6 +529,11 @@ int prior_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m, Range no
     const int te = std::min(t1, nreg);
     const int g0 = h->group_of_tile[m][t0], g1 = h->group_of_tile[m][te - 1] + 1;
     const int4* gl = reinterpret_cast<const int4*>(h->ws + L.pgroups + h->pgroups_off[m]) + g0;
+    if (c.tune & 64) {
+      const size_t deep = smem_pgroups(r) + sizeof(PriorSmemT<6>) - sizeof(PriorSmem);
+      MRA_FOR_VEC_NJ(h, CU(smem_at_least(k_prior_groups<J_, 6>, deep)));
+      MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", (k_prior_groups<J_, 6><<<g1 - g0, NT, deep, st>>>(c, gl, m))));
+    } else
     MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", k_prior_groups<J_><<<g1 - g0, NT, smem_pgroups(r), st>>>(c, gl, m)));
     t0 = te;
   }

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+run() { env "$@" python tools/profile_step.py --workload cfg5 --warm 2 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); km=d['kernels_ms']
+print(' '.join('%s=%.3f'%(k,km[k]) for k in ('prior_tiles','predict_fused','assemble_A','leaf_q')), 'sum=%.2f'%sum(km.values()), d['likelihood'])"; }
+echo base; run MRA_TUNE=0
+echo prior_6stages_2ctas; run MRA_TUNE=64
