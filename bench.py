@@ -448,13 +448,13 @@ def run_ours(args, rank, world, local_rank):
     # whole step against the roof that binds each kernel family: sum over families of max(algorithmic flop / FP64 peak,
     # algorithmic bytes / HBM peak), divided by the measured time of those launches (families below the ridge are
     # HBM-bound: counting them against the FP64 peak alone understates small-r workloads such as cfg3 / cfg4)
-    t_roof = sum(max(prof[k]["flops"] / (peak * 1e12), prof[k]["bytes"] / (hbm_peak * 1e9)) for k in kern) / args.steps
+    t_roof = sum(max(prof[k]["flops"] / (peak * 1e12), prof[k]["bytes"] / (hbm_peak * 1e9)) for k in kern)   # per step
     t_meas = sum(kern[k]["ms_per_step"] for k in kern) * 1e-3
     roofline["whole_step_binding_roof"] = {
         "roof_ms": t_roof * 1e3, "kernel_ms": t_meas * 1e3, "frac": t_roof / t_meas if t_meas > 0 else None,
         "hbm_bound_families": sorted(k for k in kern if prof[k]["bytes"] > 0 and prof[k]["flops"] / prof[k]["bytes"] < ridge)}
     for k in kern:
-        tr_k = max(prof[k]["flops"] / (peak * 1e12), prof[k]["bytes"] / (hbm_peak * 1e9)) / args.steps
+        tr_k = max(prof[k]["flops"] / (peak * 1e12), prof[k]["bytes"] / (hbm_peak * 1e9))
         kern[k]["roof_frac"] = tr_k / (kern[k]["ms_per_step"] * 1e-3) if kern[k]["ms_per_step"] > 0 else None
 
     # ---- CPU baseline (rank 0, bounded sample)
