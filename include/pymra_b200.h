@@ -121,6 +121,9 @@ int mra_build_stream_finish(mra_build_job *job, int32_t *n_nodes_out, int32_t *d
 /* Tree/knot/partition indexing computed on the host (bit-exact to MRANode.py:23-98,
  * 179-242, 289-340); copied into the handle. */
 int mra_set_structure(mra_handle *h, const mra_structure *s);
+/* Optional hint before mra_set_structure: mra_set_shard will follow, so the (unsharded) work lists need not be built
+ * first -- mra_set_structure starts them as a background job otherwise. */
+int mra_expect_shard(mra_handle *h);
 
 /* Scans the NaN pattern of obs (MRANode.py:415, np.isfinite) and sizes the device workspace.
  * obs: [N] in the caller's order.  want_predict != 0 reserves the buffers predict() needs. */

@@ -270,7 +270,9 @@ class MRATree(object):
             if mean is None:            # sharded run with gather="root" on a non-root rank
                 self._mom = (None, None)
             else:
-                self._mom = (np.matrix(mean.reshape(-1, 1)), sd)
+                # asmatrix: np.matrix(...) would COPY the 8 N bytes (8 ms at 4 M locations); the (N, 1) matrix the
+                # reference returns (MRATree.py:90-94) is a view of the page-locked result buffer here
+                self._mom = (np.asmatrix(mean.reshape(-1, 1)), sd)
             self.timings["predict"] = time.perf_counter() - t0
         return self._mom
 

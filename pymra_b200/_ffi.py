@@ -43,6 +43,7 @@ SIGNATURES = {
     "mra_build_stream_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "mra_build_stream_finish": (C.c_int, [C.c_void_p, _p32, _p32, _p64]),
     "mra_set_structure": (C.c_int, [C.c_void_p, C.POINTER(MraStructure)]),
+    "mra_expect_shard": (C.c_int, [C.c_void_p]),
     "mra_plan": (C.c_int, [C.c_void_p, _pd, C.c_int, C.POINTER(C.c_size_t)]),
     "mra_bind_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mra_plan_tree": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),

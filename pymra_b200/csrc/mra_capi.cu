@@ -60,6 +60,8 @@ struct mra_handle {
   // build_lists runs as a background job from mra_set_structure / mra_set_shard on (it depends on the tree only);
   // mra_plan joins it after its own O(N) passes over the observations
   std::future<void> lists_job;
+  bool defer_lists = false;      // mra_expect_shard: mra_set_shard will follow, do not build the unsharded lists first
+  bool lists_built = false;
   bool tree_planned = false, tree_bound = false, split_arena = false;      // two-part plan (mra_plan_tree / mra_plan_obs)
   size_t total_A = 0, total_B = 0;
   Layout lay_b{};                                                          // part B, offsets relative to its start
@@ -999,6 +1001,7 @@ void wait_lists(mra_handle* h) {
   if (h->lists_job.valid()) h->lists_job.get();
 }
 void start_lists(mra_handle* h) {
+  h->lists_built = true;
   if (std::getenv("MRA_SYNC_LISTS")) build_lists(h);
   else h->lists_job = std::async(std::launch::async, [h] { build_lists(h); });
 }
@@ -1078,8 +1081,16 @@ int mra_set_structure(mra_handle* h, const mra_structure* s) {
   h->ldv = std::max<long long>(2, ((long long)std::max(h->depth, 1) * h->r + 1) / 2 * 2);
   h->has_structure = true;
   h->planned = h->bound = h->uploaded = h->lik_done = h->pred_done = false;
-  start_lists(h);
+  h->lists_built = false;
+  if (!h->defer_lists) start_lists(h);
+  h->defer_lists = false;
   tr.mark("build_lists started");
+  return MRA_OK;
+}
+
+int mra_expect_shard(mra_handle* h) {
+  if (!h) return MRA_ERR_ARG;
+  h->defer_lists = true;
   return MRA_OK;
 }
 
@@ -1099,6 +1110,7 @@ int plan_tree_impl(mra_handle* h, int want_predict) {
   const int nn = h->n_nodes, r = h->r;
   h->want_predict = want_predict != 0;
   drop_graph(h);
+  if (!h->lists_built) start_lists(h);
   wait_lists(h);
   tr.mark("wait for build_lists");
   h->nodes.assign(nn, NodeDev{});
@@ -2122,12 +2134,21 @@ int mra_unpermute_tree_dev(mra_handle* h, void* stream, const double* dev_mean_t
 int mra_run_predict(mra_handle* h, void* stream, double* mean, double* sd) {
   if (!h || !mean || !sd) return MRA_ERR_ARG;
   DEVICE_SCOPE(h);
+  HostTrace tr("run_predict");
   int rc = mra_run_predict_dev(h, stream, nullptr, nullptr);
   if (rc) return rc;
+  tr.mark("launches");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tr.on) {
+    cudaStreamSynchronize(st);
+    tr.mark("kernels done");
+  }
   CU(cudaMemcpyAsync(mean, h->ws + h->lay.out_mean, sizeof(double) * h->N, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(sd, h->ws + h->lay.out_sd, sizeof(double) * h->N, cudaMemcpyDeviceToHost, st));
-  return check_status(h, st);
+  tr.mark("copies enqueued");
+  rc = check_status(h, st);
+  tr.mark("copies done");
+  return rc;
 }
 
 int mra_set_diagnostics(mra_handle* h, int keep_posterior_basis) {

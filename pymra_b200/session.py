@@ -43,6 +43,8 @@ class DeviceSession(object):
         st = self.lib.mra_create(C.byref(self.h), self.dev.index)
         if st != 0:
             raise _ffi.MraError(st, "mra_create failed (no usable CUDA device?)")
+        if group is not None or emulate is not None:
+            self.check(self.lib.mra_expect_shard(self.h))      # the lists are built once, by mra_set_shard
         self._set_structure()
         self.timings["set_structure"] = time.perf_counter() - t0
         self.group, self.world, self.rank, self.shard_level, self.summary = None, 1, 0, 0, None
@@ -333,9 +335,12 @@ class DeviceSession(object):
         # rate and the returned arrays are zero-copy views of it (the block is recycled once they are dropped;
         # an extra host copy out of a shared staging buffer was measured slower)
         import torch
+        t0 = time.perf_counter()
         out = torch.empty(2, self.N, dtype=torch.float64, pin_memory=True)
         host = out.numpy()
+        t1 = time.perf_counter()
         self.check(self.lib.mra_run_predict(self.h, self.stream(), _dptr(host[0]), _dptr(host[1])))
+        self.timings.update(predict_alloc=t1 - t0, predict_call=time.perf_counter() - t1)
         return host[0], host[1]
 
     def predict_dev(self, mean_t=None, sd_t=None, reduce=False):
