@@ -8,6 +8,7 @@ python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo 
 tail -3 gpurun_out/pytest_gpu_$TAG.log
 python bench.py > gpurun_out/bench_cfg5_$TAG.log 2>&1; echo bench_exit=$?
 python bench.py --workload cfg3 --no-cpu-baseline > gpurun_out/bench_cfg3_$TAG.log 2>&1; echo bench3_exit=$?
+python bench.py --workload cfg4 --steps 20 --no-cpu-baseline > gpurun_out/bench_cfg4_$TAG.log 2>&1; echo bench4_exit=$?
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_$TAG.log 2>&1; echo ref_exit=$?
 python tools/profile_step.py --workload cfg5 > gpurun_out/prof_plain_cfg5_$TAG.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
