@@ -1,0 +1,5 @@
+run() { env "$@" python tools/profile_step.py --workload cfg5 --warm 2 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); km=d['kernels_ms']
+print(' '.join('%s=%.3f'%(k,km[k]) for k in ('prior_tiles','predict_fused','assemble_A','leaf_q','leaf_gram','knot_gram')), 'sum=%.2f'%sum(km.values()), d['likelihood'])"; }
+run MRA_TUNE=0
