@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29548 bench.py --gpus 8 --steps 10 --warmup 3 --e2e-steps 5 > gpurun_out/bench_cfg5_8gpu_r05.json 2> gpurun_out/bench_cfg5_8gpu_r05.err; echo bench8_exit=$?
+tail -c 200 gpurun_out/bench_cfg5_8gpu_r05.err
