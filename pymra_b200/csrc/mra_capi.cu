@@ -191,6 +191,43 @@ struct HostTrace {
   }
 };
 
+// The large host-side vectors of a handle (work lists, row lists, permutation, node table: ~50 MB at 4 M locations) are
+// recycled across handles: a construction that follows another one in the same process (an MLE loop with the reference's
+// semantics builds a tree per evaluation) finds them allocated and page-faulted.  One set is kept.
+struct HostBuffers {
+  std::vector<std::vector<int4>> ptiles_at, pgroups_at;
+  std::vector<std::vector<int>> group_of_tile, internal_at;
+  std::vector<int4> leaf_tiles, fold_items;
+  std::vector<int> knot_rows, leaves;
+  IntBuf perm, obs_rows, unobs_rows;
+  std::vector<NodeDev> nodes;
+};
+std::mutex g_pool_mu;
+std::unique_ptr<HostBuffers> g_pool;
+
+template <class H, class B>
+void swap_buffers(H* h, B& b) {
+  h->ptiles_at.swap(b.ptiles_at);
+  h->pgroups_at.swap(b.pgroups_at);
+  h->group_of_tile.swap(b.group_of_tile);
+  h->internal_at.swap(b.internal_at);
+  h->leaf_tiles.swap(b.leaf_tiles);
+  h->fold_items.swap(b.fold_items);
+  h->knot_rows.swap(b.knot_rows);
+  h->leaves.swap(b.leaves);
+  h->perm.swap(b.perm);
+  h->obs_rows.swap(b.obs_rows);
+  h->unobs_rows.swap(b.unobs_rows);
+  h->nodes.swap(b.nodes);
+}
+
+// outer.resize(n) with every inner vector emptied but its capacity kept
+template <class T>
+void reset_levels(std::vector<std::vector<T>>& v, size_t n) {
+  v.resize(n);
+  for (auto& x : v) x.clear();
+}
+
 int fail(mra_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
@@ -727,8 +764,8 @@ void build_lists(mra_handle* h) {
   HostTrace tr("build_lists");
   const int nn = h->n_nodes, s = h->shard_level;
   const size_t nlev = (size_t)h->depth + 1;
-  h->internal_at.assign(nlev, {});
-  h->ptiles_at.assign(nlev, {});
+  reset_levels(h->internal_at, nlev);
+  reset_levels(h->ptiles_at, nlev);
   h->leaves.clear();
   h->gather_rows.clear();
   h->emit_chunks.clear();
@@ -814,8 +851,8 @@ void build_lists(mra_handle* h) {
   }
   tr.mark("tiles");
   // groups of the regular prior tiles: consecutive full tiles of one node, at most PG per group
-  h->pgroups_at.assign(h->ptiles_at.size(), {});
-  h->group_of_tile.assign(h->ptiles_at.size(), {});
+  reset_levels(h->pgroups_at, h->ptiles_at.size());
+  reset_levels(h->group_of_tile, h->ptiles_at.size());
   std::vector<std::thread> gth;
   for (size_t m = 0; m < h->ptiles_at.size(); ++m) gth.emplace_back([h, m] {
     const std::vector<int4>& tl = h->ptiles_at[m];
@@ -970,12 +1007,27 @@ int mra_create(mra_handle** out, int device) {
       return MRA_ERR_CUDA;
     }
   }
+  if (!std::getenv("MRA_NO_HOST_POOL")) {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (g_pool) {
+      swap_buffers(h, *g_pool);
+      g_pool.reset();
+    }
+  }
   *out = h;
   return MRA_OK;
 }
 
 int mra_destroy(mra_handle* h) {
   if (h && h->lists_job.valid()) h->lists_job.get();
+  if (h && !std::getenv("MRA_NO_HOST_POOL")) {
+    std::unique_ptr<HostBuffers> b(new (std::nothrow) HostBuffers());
+    if (b) {
+      swap_buffers(h, *b);
+      std::lock_guard<std::mutex> lock(g_pool_mu);
+      g_pool = std::move(b);      // the previous set, if any, is released
+    }
+  }
   if (h && h->copy_stream) {
     DevGuard g(h->device);
     cudaEventDestroy(h->copy_event);
