@@ -203,6 +203,10 @@ struct HostBuffers {
   std::vector<NodeDev> nodes;
 };
 std::mutex g_pool_mu;
+bool env_on(const char* name) {
+  const char* e = std::getenv(name);
+  return e && e[0] && e[0] != '0';
+}
 std::unique_ptr<HostBuffers> g_pool;
 
 template <class H, class B>
@@ -1007,7 +1011,7 @@ int mra_create(mra_handle** out, int device) {
       return MRA_ERR_CUDA;
     }
   }
-  if (!std::getenv("MRA_NO_HOST_POOL")) {
+  if (!env_on("MRA_NO_HOST_POOL")) {
     std::lock_guard<std::mutex> lock(g_pool_mu);
     if (g_pool) {
       swap_buffers(h, *g_pool);
@@ -1020,7 +1024,7 @@ int mra_create(mra_handle** out, int device) {
 
 int mra_destroy(mra_handle* h) {
   if (h && h->lists_job.valid()) h->lists_job.get();
-  if (h && !std::getenv("MRA_NO_HOST_POOL")) {
+  if (h && !env_on("MRA_NO_HOST_POOL")) {
     std::unique_ptr<HostBuffers> b(new (std::nothrow) HostBuffers());
     if (b) {
       swap_buffers(h, *b);

@@ -152,3 +152,47 @@ def test_emulated_shards_stream_their_parts(world):
     assert again[0] == want[0] and np.array_equal(again[1], want[1]) and np.array_equal(again[2], want[2])
     for s in sess:
         s.close()
+
+
+def test_two_part_setup_call_order_and_equivalence():
+    """mra_plan_tree / mra_bind_tree / mra_plan_obs / mra_bind_obs: the prior levels may run before the observation half
+    is bound, everything else is refused until then; results equal the one-piece set-up bit for bit, also for a refit
+    (plain pass on the split arena) and for parts whose prior levels ran early in any order."""
+    import torch
+    import pymra_b200.MRATools as mt
+    from pymra_b200 import _ffi
+    from pymra_b200.covariance import introspect
+    from pymra_b200.session import DeviceSession
+    from pymra_b200.structure import build_structure
+    locs, y = make(200)
+    np.random.seed(7)
+    st = build_structure(locs, 16, 3, 4, 9)
+    cov = introspect(lambda a, b: mt.Matern32(a, b, l=0.3, sig=1.0), 2)
+    ref = DeviceSession(st, locs, y)
+    ref.set_params(cov, 1e-2)
+    want = ref.likelihood()
+    wm, ws = ref.predict()
+    wm, ws = wm.copy(), ws.copy()
+    ref.close()
+    dev = torch.device("cuda")
+    staged = (torch.from_numpy(np.ascontiguousarray(locs)).to(dev), torch.from_numpy(np.ascontiguousarray(y).reshape(-1)).to(dev))
+    s = DeviceSession(st, locs, y, staged=staged, two_part=True)
+    assert s._pending_obs is not None and s.ws_obs is None
+    s.set_params(cov, 1e-2)
+    s.stream_begin()
+    with pytest.raises(_ffi.MraError):
+        s.stream_part(0)                       # leaf terms need the observation half
+    s.stream_part_prior(2)
+    s.stream_part_prior(0)
+    with pytest.raises(_ffi.MraError):
+        s.stream_part_prior(2)                 # twice
+    s.finish_plan()
+    assert s._pending_obs is None and s.ws_obs is not None
+    for part in (3, 0, 2, 1):
+        s.stream_part(part)
+    s.stream_end()
+    assert s.fetch_likelihood() == want
+    gm, gs = s.predict()
+    assert np.array_equal(gm, wm) and np.array_equal(gs, ws)
+    assert s.likelihood() == want              # plain pass on the two allocations
+    s.close()
