@@ -420,6 +420,7 @@ cudaError_t configure_vec_nj(int r, int depth) {
   SET_((k_prior_tiles<V_, J_>), smem_prior(r));
   if (V_ == 2) {
     SET_((k_prior_groups<J_>), smem_pgroups(r));
+    SET_((k_prior_groups<J_, true>), smem_pgroups(r));
   }
   SET_((k_node_gt<V_, J_>), GS1);
   SET_((k_predict_fused<V_, J_>), smem_predict(r, depth));
@@ -572,12 +573,14 @@ int prior_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m, Range no
     const int te = std::min(t1, nreg);
     const int g0 = h->group_of_tile[m][t0], g1 = h->group_of_tile[m][te - 1] + 1;
     const int4* gl = reinterpret_cast<const int4*>(h->ws + L.pgroups + h->pgroups_off[m]) + g0;
-    if (c.tune & 64) {
-      const size_t deep = smem_pgroups(r) + sizeof(PriorSmemT<6>) - sizeof(PriorSmem);
-      MRA_FOR_VEC_NJ(h, CU(smem_at_least(k_prior_groups<J_, 6>, deep)));
-      MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", (k_prior_groups<J_, 6><<<g1 - g0, NT, deep, st>>>(c, gl, m))));
-    } else
-    MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", k_prior_groups<J_><<<g1 - g0, NT, smem_pgroups(r), st>>>(c, gl, m)));
+    // r a multiple of 16 (one column tile): the level's covariance block is evaluated ahead of the product, into the
+    // columns of V the product overwrites (k_cov_fill); MRA_TUNE bit 7 keeps the evaluation inside the product (A/B)
+    if (r % KC == 0 && r <= TB && !(c.tune & 128)) {
+      LAUNCH("prior_tiles", k_cov_fill<<<g1 - g0, 256, sizeof(double) * 2 * r, st>>>(c, gl, m));
+      MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", (k_prior_groups<J_, true><<<g1 - g0, NT, smem_pgroups(r), st>>>(c, gl, m))));
+    } else {
+      MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", k_prior_groups<J_><<<g1 - g0, NT, smem_pgroups(r), st>>>(c, gl, m)));
+    }
     t0 = te;
   }
   if (t0 < t1) {
