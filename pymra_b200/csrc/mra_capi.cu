@@ -576,7 +576,17 @@ int prior_level(mra_handle* h, cudaStream_t st, const DevCtx& c, int m, Range no
     // r a multiple of 16 (one column tile): the level's covariance block is evaluated ahead of the product, into the
     // columns of V the product overwrites (k_cov_fill); MRA_TUNE bit 7 keeps the evaluation inside the product (A/B)
     if (r % KC == 0 && r <= TB && !(c.tune & 128)) {
-      LAUNCH("prior_tiles", k_cov_fill<<<g1 - g0, 256, sizeof(double) * 2 * r, st>>>(c, gl, m));
+      {
+        // the family is a launch-time constant except inside a captured graph (refit may change it between replays)
+        const int fam = h->capturing ? -1 : h->cov.family;
+        const size_t csm = sizeof(double) * 2 * r;
+        ProfScope ps_(h, st, "prior_tiles");
+        if (fam == 0) k_cov_fill<0><<<g1 - g0, 256, csm, st>>>(c, gl, m);
+        else if (fam == 1) k_cov_fill<1><<<g1 - g0, 256, csm, st>>>(c, gl, m);
+        else if (fam == 2) k_cov_fill<2><<<g1 - g0, 256, csm, st>>>(c, gl, m);
+        else if (fam == 3) k_cov_fill<3><<<g1 - g0, 256, csm, st>>>(c, gl, m);
+        else k_cov_fill<-1><<<g1 - g0, 256, csm, st>>>(c, gl, m);
+      }
       MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", (k_prior_groups<J_, true><<<g1 - g0, NT, smem_pgroups(r), st>>>(c, gl, m))));
     } else {
       MRA_FOR_VEC_NJ(h, LAUNCH("prior_tiles", k_prior_groups<J_><<<g1 - g0, NT, smem_pgroups(r), st>>>(c, gl, m)));
