@@ -638,7 +638,14 @@ int leaf_predict_terms(mra_handle* h, cudaStream_t st, const DevCtx& c, Range rg
   if (h->leaf_v2) {
     if (nbu > 0) {
       if (h->leaf_wide)
-        LAUNCH("leaf_q", k_leaf_q2<<<(unsigned)nleaf * nbu, NTW, smem_leafq2(h->max_leaf_obs), st>>>(c, leaf_list, nbu, h->max_leaf_obs));
+      {
+        // leaves with at most 128 observations (one super tile): the covariance block is evaluated ahead of the product, into
+        // the rows of QT the product overwrites (MRA_TUNE bit 8: always inside the product)
+        const int pre = (c.tune & 256) ? 0 : 1;
+        if (pre)
+          LAUNCH("leaf_q", k_leaf_cov_fill<<<(unsigned)nleaf * nbu, 256, sizeof(double) * 2 * h->max_leaf_obs, st>>>(c, leaf_list, nbu, h->max_leaf_obs));
+        LAUNCH("leaf_q", k_leaf_q2<<<(unsigned)nleaf * nbu, NTW, smem_leafq2(h->max_leaf_obs), st>>>(c, leaf_list, nbu, h->max_leaf_obs, pre));
+      }
       else
         MRA_FOR_VEC(h, LAUNCH("leaf_q", k_leaf_q<V_><<<(unsigned)nleaf * nbu, NT, smem_leafq(h->max_leaf_obs), st>>>(
                                             c, leaf_list, nbu, h->max_leaf_obs)));
