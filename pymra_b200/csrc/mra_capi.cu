@@ -359,6 +359,11 @@ size_t smem_predict(int r, int depth) {
          sizeof(int) * MAX_LEVELS + sizeof(long long) * 2 * MAX_LEVELS + pad;
 }
 
+size_t smem_predict2(int r, int depth) {
+  return sizeof(double) * 2 * NSTAGE * TB * KC + sizeof(double) * ((size_t)2 * TB + (size_t)std::max(depth, 1) * r) +
+         sizeof(long long) * 2 * MAX_LEVELS;
+}
+
 // Kernels are instantiated for VEC = 2 (16-byte cp.async, even r) and VEC = 1 (odd r).
 #define MRA_FOR_VEC(h, expr)         \
   do {                               \
@@ -763,6 +768,12 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
       MRA_FOR_VEC(h, LAUNCH("fold", k_fold<V_><<<(unsigned)h->fold_items.size(), NT, GS1 + sizeof(long long) * MAX_LEVELS, st>>>(
                                         c, at<int4>(h, L.fold))));
     if (!h->leaf_tiles.empty())
+    if (r % KC == 0 && r <= TB && !(c.tune & 512)) {      // table-free loader, 4 CTAs per SM (MRA_TUNE bit 9: the general kernel)
+      const size_t sm2 = smem_predict2(r, h->depth);
+      MRA_FOR_VEC_NJ(h, CU(smem_at_least(k_predict_fused2<J_>, sm2)));
+      MRA_FOR_VEC_NJ(h, LAUNCH("predict_fused", k_predict_fused2<J_><<<(unsigned)h->leaf_tiles.size(), NT, sm2, st>>>(
+                                                 c, at<int4>(h, L.ltiles), h->depth)));
+    } else
       MRA_FOR_VEC_NJ(h, LAUNCH("predict_fused", k_predict_fused<V_, J_><<<(unsigned)h->leaf_tiles.size(), NT, smem_predict(r, h->depth), st>>>(
                                                  c, at<int4>(h, L.ltiles), h->depth)));
     h->pred_done = true;   // V now holds the posterior-updated basis; results stay cached in mean/var
