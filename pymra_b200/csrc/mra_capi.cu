@@ -359,8 +359,8 @@ size_t smem_predict(int r, int depth) {
          sizeof(int) * MAX_LEVELS + sizeof(long long) * 2 * MAX_LEVELS + pad;
 }
 
-size_t smem_predict2(int r, int depth) {
-  return sizeof(double) * 2 * NSTAGE * TB * KC + sizeof(double) * ((size_t)2 * TB + (size_t)std::max(depth, 1) * r) +
+size_t smem_predict2(int r, int depth, int tile_rows) {
+  return sizeof(double) * NSTAGE * (tile_rows + TB) * KC + sizeof(double) * ((size_t)2 * tile_rows + (size_t)std::max(depth, 1) * r) +
          sizeof(long long) * 2 * MAX_LEVELS;
 }
 
@@ -768,11 +768,19 @@ int launch_predict(mra_handle* h, cudaStream_t st, double* dev_mean, double* dev
       MRA_FOR_VEC(h, LAUNCH("fold", k_fold<V_><<<(unsigned)h->fold_items.size(), NT, GS1 + sizeof(long long) * MAX_LEVELS, st>>>(
                                         c, at<int4>(h, L.fold))));
     if (!h->leaf_tiles.empty())
-    if (r % KC == 0 && r <= TB && !(c.tune & 512)) {      // table-free loader, 4 CTAs per SM (MRA_TUNE bit 9: the general kernel)
-      const size_t sm2 = smem_predict2(r, h->depth);
-      MRA_FOR_VEC_NJ(h, CU(smem_at_least(k_predict_fused2<J_>, sm2)));
-      MRA_FOR_VEC_NJ(h, LAUNCH("predict_fused", k_predict_fused2<J_><<<(unsigned)h->leaf_tiles.size(), NT, sm2, st>>>(
-                                                 c, at<int4>(h, L.ltiles), h->depth)));
+    if (r % KC == 0 && r <= TB && !(c.tune & 512)) {      // table-free loader (MRA_TUNE bit 9: the general kernel)
+      const int nt = (int)h->leaf_tiles.size();
+      if (!(c.tune & 1024)) {                              // 64-row tiles, 4 CTAs per SM
+        const size_t sm2 = smem_predict2(r, h->depth, TB);
+        MRA_FOR_VEC_NJ(h, CU(smem_at_least((k_predict_fused2<J_, 64>), sm2)));
+        MRA_FOR_VEC_NJ(h, LAUNCH("predict_fused", (k_predict_fused2<J_, 64><<<(unsigned)nt, 128, sm2, st>>>(
+                                                   c, at<int4>(h, L.ltiles), nt, h->depth))));
+      } else {      // MRA_TUNE bit 10: 128 rows per CTA (pairs of tiles share their B chunks) -- measured slower, 44.8 vs 41.5 ms
+        const size_t sm2 = smem_predict2(r, h->depth, 2 * TB);
+        MRA_FOR_VEC_NJ(h, CU(smem_at_least((k_predict_fused2<J_, 128>), sm2)));
+        MRA_FOR_VEC_NJ(h, LAUNCH("predict_fused", (k_predict_fused2<J_, 128><<<(unsigned)((nt + 1) / 2), 256, sm2, st>>>(
+                                                   c, at<int4>(h, L.ltiles), nt, h->depth))));
+      }
     } else
       MRA_FOR_VEC_NJ(h, LAUNCH("predict_fused", k_predict_fused<V_, J_><<<(unsigned)h->leaf_tiles.size(), NT, smem_predict(r, h->depth), st>>>(
                                                  c, at<int4>(h, L.ltiles), h->depth)));
