@@ -135,7 +135,9 @@ __device__ __forceinline__ void stage_load(double* st, const double* const* rows
 // J0: first column group that is computed.  A chunk of a LOWER-TRIANGULAR B operand (B[j][k] = 0 for k > j: Linv,
 // Lp^-1) whose k range starts at 16 t has only zeros in the column groups below 2 t; chunk_mma_tri picks the unrolled
 // variant for that chunk with one warp-uniform switch, so the DMMA stream itself stays free of predicates.
-template <int NJ, int J0 = 0, int J1 = NJ, class GA, class GB>
+// KS: k-steps (of 4) that are run; the last chunk of a K segment whose length is not a multiple of 16 holds zero-filled
+// columns beyond its end, and chunk_mma_tail picks the variant that stops after the steps that hold data.
+template <int NJ, int J0 = 0, int J1 = NJ, int KS = KC / 4, class GA, class GB>
 __device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows = TB, int ncols = TB, int wg = -1) {
   // wg: the 16-row group this warp owns (default: its index).  Kernels whose warps do unequal work (ragged or
   // triangular tiles) rotate it with the CTA index so that the idle tensor pipe differs between co-resident CTAs.
@@ -145,7 +147,7 @@ __device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows
   (void)ncols;
   const int g = lane >> 2, q = lane & 3;
 #pragma unroll
-  for (int ks = 0; ks < KC; ks += 4) {
+  for (int ks = 0; ks < 4 * KS; ks += 4) {
     double a[2], b[NJ];
 #pragma unroll
     for (int i = 0; i < 2; ++i) a[i] = ga(wm + i * 8 + g, ks + q);
@@ -156,6 +158,15 @@ __device__ __forceinline__ void chunk_mma(AccT<NJ>& acc, GA ga, GB gb, int mrows
 #pragma unroll
       for (int j = J0; j < J1; ++j) dmma884(acc.v[i][j], a[i], b[j]);
   }
+}
+
+// kvalid: columns of the chunk that hold data (1 .. 16)
+template <int NJ, class GA, class GB>
+__device__ __forceinline__ void chunk_mma_tail(AccT<NJ>& acc, GA ga, GB gb, int kvalid, int mrows = TB, int wg = -1) {
+  if (kvalid > 12) return chunk_mma<NJ, 0, NJ, 4>(acc, ga, gb, mrows, TB, wg);
+  if (kvalid > 8) return chunk_mma<NJ, 0, NJ, 3>(acc, ga, gb, mrows, TB, wg);
+  if (kvalid > 4) return chunk_mma<NJ, 0, NJ, 2>(acc, ga, gb, mrows, TB, wg);
+  chunk_mma<NJ, 0, NJ, 1>(acc, ga, gb, mrows, TB, wg);
 }
 
 // Diagonal tile of a symmetric product (64 x 64 tile, NJ = 8): the warp owning row group wg only needs the column
@@ -344,6 +355,7 @@ __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB
     cp_async_commit();
   }
   int buf = 0;
+  int cseg = 0, ck0 = 0;       // consumer cursor: segment and k offset of the chunk being multiplied
   for (int kt = 0; kt < nk; ++kt) {
     cp_async_wait<NSTAGE - 2>();
     __syncthreads();
@@ -353,6 +365,12 @@ __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB
       if (kt + NSTAGE - 1 < nk) load_next(nb);
       cp_async_commit();
     }
+    while (ck0 >= sm.seg_k[cseg]) {      // nk counts only chunks of segments that exist, so cseg stays below nseg
+      ++cseg;
+      ck0 = 0;
+    }
+    const int kvalid = sm.seg_k[cseg] - ck0;      // > 0; a segment's last chunk may hold fewer than 16 columns
+    ck0 += KC;
     const double* sa = sm.a[buf];
     const double* sb = sm.b[buf];
     auto ga = [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; };
@@ -360,6 +378,7 @@ __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB
     if (TRI && (unsigned)(kt - tri_kt0) < (unsigned)tri_nk) chunk_mma_tri(acc, ga, gb, kt - tri_kt0, mrows);
     else if constexpr (NJ == 8 && !TRI && !GEN) {
       if (lower) chunk_mma_lower(acc, ga, gb, mrows, wg);
+      else if (kvalid <= 12) chunk_mma_tail(acc, ga, gb, kvalid, mrows, wg);
       else chunk_mma(acc, ga, gb, mrows, ncols, wg);
     } else chunk_mma(acc, ga, gb, mrows, ncols, wg);
     if (++buf == NSTAGE) buf = 0;
@@ -491,9 +510,12 @@ __device__ __forceinline__ void tile_gemm_kmajorB_rows(AccT<NJ>& acc, int K, FA 
     }
     const double* sa = sm.a[buf];
     const double* sb = sm.b[buf];
-    if (kt * KC <= klast)
-      chunk_mma(acc, [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; },
-                [&](int col, int kk) -> double { return sb[kstage_pos(kk, col)]; }, mrows, TB, wg);
+    if (kt * KC <= klast) {
+      auto ga = [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; };
+      auto gb = [&](int col, int kk) -> double { return sb[kstage_pos(kk, col)]; };
+      if (K - kt * KC <= 12) chunk_mma_tail(acc, ga, gb, K - kt * KC, mrows, wg);      // last chunk: K mod 16 columns hold data
+      else chunk_mma(acc, ga, gb, mrows, TB, wg);
+    }
     if (++buf == NSTAGE) buf = 0;
   }
   cp_async_wait<0>();
