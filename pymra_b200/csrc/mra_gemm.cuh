@@ -355,7 +355,6 @@ __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB
     cp_async_commit();
   }
   int buf = 0;
-  int cseg = 0, ck0 = 0;       // consumer cursor: segment and k offset of the chunk being multiplied
   for (int kt = 0; kt < nk; ++kt) {
     cp_async_wait<NSTAGE - 2>();
     __syncthreads();
@@ -365,20 +364,15 @@ __device__ __forceinline__ void tile_gemm_seg(AccT<NJ>& acc, int nseg, FA fa, FB
       if (kt + NSTAGE - 1 < nk) load_next(nb);
       cp_async_commit();
     }
-    while (ck0 >= sm.seg_k[cseg]) {      // nk counts only chunks of segments that exist, so cseg stays below nseg
-      ++cseg;
-      ck0 = 0;
-    }
-    const int kvalid = sm.seg_k[cseg] - ck0;      // > 0; a segment's last chunk may hold fewer than 16 columns
-    ck0 += KC;
     const double* sa = sm.a[buf];
     const double* sb = sm.b[buf];
     auto ga = [&](int row, int kk) -> double { return sa[stage_pos(row, kk)]; };
     auto gb = [&](int row, int kk) -> double { return sb[stage_pos(row, kk)]; };
     if (TRI && (unsigned)(kt - tri_kt0) < (unsigned)tri_nk) chunk_mma_tri(acc, ga, gb, kt - tri_kt0, mrows);
     else if constexpr (NJ == 8 && !TRI && !GEN) {
+      // (stopping the last chunk of a ragged segment after the k-steps that hold data -- chunk_mma_tail, as the fused
+      // predict and leaf_ut do -- made assemble_A slower here: 17.8 vs 17.7 ms)
       if (lower) chunk_mma_lower(acc, ga, gb, mrows, wg);
-      else if (kvalid <= 12) chunk_mma_tail(acc, ga, gb, kvalid, mrows, wg);
       else chunk_mma(acc, ga, gb, mrows, ncols, wg);
     } else chunk_mma(acc, ga, gb, mrows, ncols, wg);
     if (++buf == NSTAGE) buf = 0;
