@@ -27,7 +27,7 @@ COLS = [
 ]
 
 
-FAMILY = {"k_prior_tiles": "prior_tiles", "k_prior_groups": "prior_tiles", "k_cov_fill": "prior_tiles", "k_predict_fused": "predict_fused",
+FAMILY = {"k_prior_tiles": "prior_tiles", "k_prior_groups": "prior_tiles", "k_cov_fill": "prior_tiles", "k_leaf_cov_fill": "leaf_q", "k_predict_fused": "predict_fused",
           "k_assemble_A": "assemble_A", "k_leaf_solve": "leaf_solve", "k_leaf_gram": "leaf_gram",
           "k_leaf_chol": "leaf_chol", "k_leaf_upd": "leaf_upd", "k_leaf_trsm": "leaf_trsm", "k_leaf_qobs": "leaf_qobs",
           "k_leaf_q": "leaf_q", "k_leaf_linv": "leaf_linv", "k_leaf_ut2": "leaf_ut",
