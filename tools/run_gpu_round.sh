@@ -16,7 +16,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 echo ncu1_exit=$?
 python tools/profile_step.py --workload cfg5 > gpurun_out/prof_plain2_cfg5_$TAG.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k "regex:$KREGEX" -c 64 -o gpurun_out/prof_cfg5_$TAG -f python tools/profile_step.py --workload cfg5 > gpurun_out/ncu2_$TAG.log 2>&1
+  -k "regex:$KREGEX" -c 96 -o gpurun_out/prof_cfg5_$TAG -f python tools/profile_step.py --workload cfg5 > gpurun_out/ncu2_$TAG.log 2>&1
 echo ncu2_exit=$?
 if [ -f gpurun_out/prof_cfg5_$TAG.ncu-rep ]; then
   ncu -i gpurun_out/prof_cfg5_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_cfg5_${TAG}_raw.csv 2>/dev/null
