@@ -360,7 +360,8 @@ size_t smem_predict(int r, int depth) {
 }
 
 size_t smem_predict2(int r, int depth, int tile_rows) {
-  return sizeof(double) * NSTAGE * (tile_rows + TB) * KC + sizeof(double) * ((size_t)2 * tile_rows + (size_t)std::max(depth, 1) * r) +
+  static const size_t pad = env_pad("MRA_SMEM_PAD_PREDICT");
+  return pad + sizeof(double) * NSTAGE * (tile_rows + TB) * KC + sizeof(double) * ((size_t)2 * tile_rows + (size_t)std::max(depth, 1) * r) +
          sizeof(long long) * 2 * MAX_LEVELS;
 }
 
